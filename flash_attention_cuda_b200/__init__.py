@@ -1,0 +1,185 @@
+"""flash_attention_cuda_b200 -- host-side binding of libflashattn_b200.so (B200 / sm_100a).
+
+The product is the C-ABI shared library (include/flash_attn.h); this module is the thin
+ctypes layer the tests and bench.py use to call it with torch tensors.  It mirrors the
+reference's launcher surface, ``flash_attention_v9_dispatch`` (reference
+flash_attention.cu:606-663): FP16 ``[B, H, N, D]`` tensors, scale ``1/sqrt(D)``, optional
+causal mask, launch on the current stream.
+
+There is no fallback: if the CUDA library is missing or fails to load, importing the symbols
+raises.  Nothing in here touches ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_PKG_DIR)
+LIB_PATH = os.path.join(_PKG_DIR, "libflashattn_b200.so")
+
+FA_OK = 0
+ERRORS = {
+    -1: "FA_ERR_BAD_HEAD_DIM",
+    -2: "FA_ERR_NULL_PTR",
+    -3: "FA_ERR_MISALIGNED",
+    -4: "FA_ERR_BAD_SHAPE",
+    -5: "FA_ERR_UNSUPPORTED_ARCH",
+    -6: "FA_ERR_TENSORMAP",
+    -7: "FA_ERR_WORKSPACE",
+}
+
+# every symbol include/flash_attn.h declares
+EXPORTED_SYMBOLS = (
+    "flash_attn_fwd",
+    "flash_attn_fwd_ex",
+    "flash_attn_finalize",
+    "flash_attn_fwd_host",
+    "flash_attn_get_kernel_info",
+    "flash_attn_launch_count",
+    "flash_attn_destroy",
+    "flash_attn_error_string",
+    "flash_attn_version",
+)
+
+
+class FlashAttnError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"flash_attn: {msg} (code {code})")
+        self.code = code
+
+
+class KernelInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "regs_per_thread", "local_bytes_per_thread", "static_smem_bytes", "dynamic_smem_bytes",
+        "threads_per_cta", "ctas", "tmem_columns", "kv_stages", "work_items", "num_sms")]
+
+
+def build(force: bool = False) -> str:
+    """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(_PKG_DIR, "csrc", f) for f in ("fa_api.cu", "fa_fwd_sm100.cuh", "sm100_ptx.cuh")]
+    srcs.append(os.path.join(_REPO, "include", "flash_attn.h"))
+    if not force and os.path.exists(LIB_PATH):
+        if all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs if os.path.exists(s)):
+            return LIB_PATH
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", srcs[0], "-o", LIB_PATH]
+    subprocess.run(cmd, check=True, cwd=_REPO)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libflashattn_b200.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `make` or flash_attention_cuda_b200.build(); "
+            "there is no CPU or PyTorch fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+    L.flash_attn_fwd.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    L.flash_attn_fwd.restype = ci
+    L.flash_attn_fwd_ex.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ll, ll, ci, vp]
+    L.flash_attn_fwd_ex.restype = ci
+    L.flash_attn_finalize.argtypes = [vp, vp, vp, ll, ci, vp]
+    L.flash_attn_finalize.restype = ci
+    L.flash_attn_fwd_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci]
+    L.flash_attn_fwd_host.restype = ci
+    L.flash_attn_get_kernel_info.argtypes = [ci, ci, ci, ci, ci, ctypes.POINTER(KernelInfo)]
+    L.flash_attn_get_kernel_info.restype = ci
+    L.flash_attn_launch_count.argtypes = []
+    L.flash_attn_launch_count.restype = ctypes.c_ulonglong
+    L.flash_attn_destroy.argtypes = []
+    L.flash_attn_destroy.restype = None
+    L.flash_attn_error_string.argtypes = [ci]
+    L.flash_attn_error_string.restype = ctypes.c_char_p
+    L.flash_attn_version.argtypes = []
+    L.flash_attn_version.restype = ctypes.c_char_p
+    L.flash_attn_debug_work_item.argtypes = [ci, ci, ci, ci, ci, ci, ci, ll] + [ctypes.POINTER(ci)] * 5
+    L.flash_attn_debug_work_item.restype = ci
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != FA_OK:
+        raise FlashAttnError(rc, lib().flash_attn_error_string(rc).decode())
+
+
+def _stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def flash_attn_fwd(q, k, v, causal: bool = True, out=None, stream=None):
+    """O = softmax(Q K^T / sqrt(D) [+ causal mask]) V for FP16 CUDA tensors [B, H, N, D].
+
+    Same contract as the reference dispatcher (flash_attention.cu:606-663); enqueues on the
+    current (or given) torch stream and returns the output tensor without synchronising."""
+    import torch
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise ValueError("flash_attn_fwd needs CUDA tensors (there is no CPU path)")
+    if q.dtype != torch.float16 or k.dtype != torch.float16 or v.dtype != torch.float16:
+        raise TypeError("flash_attn_fwd takes float16 tensors")
+    if q.dim() != 4 or q.shape != k.shape or q.shape != v.shape:
+        raise ValueError("q, k, v must all be [B, H, N, D]")
+    if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+        raise ValueError("q, k, v must be contiguous [B, H, N, D]")
+    B, H, N, D = q.shape
+    if out is None:
+        out = torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        rc = lib().flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                  B, H, N, D, 1 if causal else 0, _stream_ptr(stream))
+    check(rc)
+    return out
+
+
+def flash_attn_fwd_partial(q, k, v, o_partial, ml, causal: bool, q_offset: int, kv_offset: int,
+                           accumulate: bool, stream=None):
+    """One K/V block of a longer sequence -> (o_partial fp32, ml) partial state (include/flash_attn.h)."""
+    B, H, Nq, D = q.shape
+    Nkv = k.shape[2]
+    import torch
+    with torch.cuda.device(q.device):
+        rc = lib().flash_attn_fwd_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), o_partial.data_ptr(),
+                                     ml.data_ptr(), B, H, Nq, Nkv, D, 1 if causal else 0,
+                                     q_offset, kv_offset, 1 if accumulate else 0, _stream_ptr(stream))
+    check(rc)
+
+
+def flash_attn_finalize(o_partial, ml, out, stream=None):
+    import torch
+    rows = o_partial.numel() // o_partial.shape[-1]
+    with torch.cuda.device(out.device):
+        rc = lib().flash_attn_finalize(o_partial.data_ptr(), ml.data_ptr(), out.data_ptr(), rows,
+                                       o_partial.shape[-1], _stream_ptr(stream))
+    check(rc)
+    return out
+
+
+def kernel_info(B: int, H: int, N: int, D: int, causal: bool) -> dict:
+    info = KernelInfo()
+    check(lib().flash_attn_get_kernel_info(B, H, N, D, 1 if causal else 0, ctypes.byref(info)))
+    return {n: getattr(info, n) for n, _ in KernelInfo._fields_}
+
+
+def launch_count() -> int:
+    return int(lib().flash_attn_launch_count())
+
+
+def work_item(w: int, B: int, H: int, Nq: int, Nkv: int, D: int, causal: bool, shift: int = 0):
+    """Host mirror of the device work decomposition (scheduler tests)."""
+    vals = [ctypes.c_int() for _ in range(5)]
+    rc = lib().flash_attn_debug_work_item(w, B, H, Nq, Nkv, D, 1 if causal else 0, shift,
+                                          *[ctypes.byref(x) for x in vals])
+    check(rc)
+    total, bh, q0, n0, n1 = (x.value for x in vals)
+    return {"total": total, "bh": bh, "q0": q0, "n0": n0, "n1": n1}

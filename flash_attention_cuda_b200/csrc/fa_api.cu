@@ -1,0 +1,293 @@
+// fa_api.cu -- host launcher behind the C ABI in include/flash_attn.h.
+//
+// Replaces the reference's flash_attention_v9_dispatch (flash_attention.cu:606-663): argument
+// validation (the reference has none), TMA descriptors for Q/K/V, one persistent launch.
+// The reference's four-tier (causal x seq>=2048) template dispatch (FA.cu:620-661) collapses to
+// one kernel per head_dim: tile shapes are fixed by the tcgen05 instruction shape (M=128) and the
+// work loop adapts to the sequence length at run time.
+#include "../../include/flash_attn.h"
+
+#include <atomic>
+#include <cstring>
+#include <mutex>
+
+#include "fa_fwd_sm100.cuh"
+
+namespace {
+
+constexpr int kMaxDevices = 64;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+std::atomic<unsigned long long> g_launches{0};
+std::once_flag g_encode_once;
+EncodeTiledFn g_encode = nullptr;
+
+struct DeviceState {
+    std::once_flag once;
+    int ok = 0;           // cudaSuccess when attributes are set
+    int num_sms = 0;
+    int cc_major = 0;
+    // staging buffers for flash_attn_fwd_host
+    std::mutex host_mu;
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaStream_t host_stream = nullptr;
+};
+DeviceState g_dev[kMaxDevices];
+
+void load_encode_fn() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+template <int D>
+int set_kernel_attrs() {
+    return (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fa::Cfg<D>::kSmemBytes);
+}
+
+// Per-device one-time setup.  Re-entrant from several host threads (one per GPU in the
+// multi-GPU harness): everything is guarded by the device's once_flag.
+DeviceState* device_state(int* err) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { *err = (int)e; return nullptr; }
+    if (dev < 0 || dev >= kMaxDevices) { *err = FA_ERR_UNSUPPORTED_ARCH; return nullptr; }
+    DeviceState* st = &g_dev[dev];
+    std::call_once(st->once, [st, dev]() {
+        cudaDeviceProp prop;
+        cudaError_t e2 = cudaGetDeviceProperties(&prop, dev);
+        if (e2 != cudaSuccess) { st->ok = (int)e2; return; }
+        st->num_sms = prop.multiProcessorCount;
+        st->cc_major = prop.major;
+        if (prop.major != 10) { st->ok = FA_ERR_UNSUPPORTED_ARCH; return; }
+        int r = set_kernel_attrs<128>();
+        if (r == 0) r = set_kernel_attrs<64>();
+        st->ok = r;
+    });
+    if (st->ok != 0) { *err = st->ok; return nullptr; }
+    return st;
+}
+
+// [BH, N, D] fp16, box = 64 halves x 128 rows x 1 head, 128-byte swizzle; rows past N read as zero.
+int make_tmap(CUtensorMap* tm, const void* base, int BH, int N, int D) {
+    std::call_once(g_encode_once, load_encode_fn);
+    if (!g_encode) return FA_ERR_TENSORMAP;
+    cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)BH};
+    cuuint64_t gstride[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)fa::kBlockN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? FA_OK : FA_ERR_TENSORMAP;
+}
+
+int validate(const void* q, const void* k, const void* v, const void* o, int B, int H, int Nq, int Nkv, int D) {
+    if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+    if (!q || !k || !v || !o) return FA_ERR_NULL_PTR;
+    if (B < 1 || H < 1 || Nq < 1 || Nkv < 1) return FA_ERR_BAD_SHAPE;
+    if ((long long)B * H > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
+    if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) & 15u) != 0) return FA_ERR_MISALIGNED;
+    return FA_OK;
+}
+
+fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shift) {
+    fa::Params p;
+    memset(&p, 0, sizeof p);
+    p.Nq = Nq; p.Nkv = Nkv; p.BH = BH;
+    p.causal = causal ? 1 : 0;
+    if (shift > 0x3fffffffLL) shift = 0x3fffffffLL;
+    if (shift < -0x3fffffffLL) shift = -0x3fffffffLL;
+    p.shift = (int)shift;
+    p.nqp = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
+    const long long tw = (long long)BH * p.nqp;
+    p.total_work = (int)tw;
+    p.scale = 1.0f / sqrtf((float)D);             // FA.cu:612
+    p.scale_log2 = p.scale * 1.4426950408889634f;
+    return p;
+}
+
+template <int D>
+int launch(const DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+           const fa::Params& p, cudaStream_t stream) {
+    int grid = p.total_work < st->num_sms ? p.total_work : st->num_sms;
+    if (grid < 1) grid = 1;
+    fa::fa_fwd_kernel<D><<<grid, fa::kNumThreads, fa::Cfg<D>::kSmemBytes, stream>>>(tq, tk, tv, p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();   // FA.cu:662
+}
+
+int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaStream_t stream) {
+    int err = 0;
+    DeviceState* st = device_state(&err);
+    if (!st) return err;
+    if ((long long)p.BH * p.nqp > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
+    CUtensorMap tq, tk, tv;
+    int rc;
+    if ((rc = make_tmap(&tq, q, p.BH, p.Nq, D)) != FA_OK) return rc;
+    if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D)) != FA_OK) return rc;
+    if ((rc = make_tmap(&tv, v, p.BH, p.Nkv, D)) != FA_OK) return rc;
+    return D == 128 ? launch<128>(st, tq, tk, tv, p, stream) : launch<64>(st, tq, tk, tv, p, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int flash_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int H, int N, int D, int causal,
+                   void* stream) {
+    int rc = validate(q, k, v, o, B, H, N, N, D);
+    if (rc != FA_OK) return rc;
+    fa::Params p = make_params(B * H, N, N, D, causal, 0);
+    p.o = static_cast<__half*>(o);
+    return run(q, k, v, p, D, static_cast<cudaStream_t>(stream));
+}
+
+int flash_attn_fwd_ex(const void* q, const void* k, const void* v, float* o_partial, float* ml, int B, int H,
+                      int Nq, int Nkv, int D, int causal, long long q_offset, long long kv_offset, int accumulate,
+                      void* stream) {
+    int rc = validate(q, k, v, o_partial, B, H, Nq, Nkv, D);
+    if (rc != FA_OK) return rc;
+    if (!ml) return FA_ERR_NULL_PTR;
+    fa::Params p = make_params(B * H, Nq, Nkv, D, causal, q_offset - kv_offset);
+    p.o_partial = o_partial;
+    p.ml = ml;
+    p.partial_mode = 1;
+    p.accumulate = accumulate ? 1 : 0;
+    return run(q, k, v, p, D, static_cast<cudaStream_t>(stream));
+}
+
+int flash_attn_finalize(const float* o_partial, const float* ml, void* o, long long rows, int D, void* stream) {
+    if (!o_partial || !ml || !o) return FA_ERR_NULL_PTR;
+    if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+    if (rows < 1) return FA_ERR_BAD_SHAPE;
+    const long long threads = rows * (D / 4);
+    const int block = 256;
+    const long long grid = (threads + block - 1) / block;
+    if (grid > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
+    fa::fa_finalize_kernel<<<(unsigned)grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        o_partial, ml, static_cast<__half*>(o), rows, D);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho, int B, int H, int N, int D,
+                        int causal) {
+    if (!hq || !hk || !hv || !ho) return FA_ERR_NULL_PTR;
+    if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+    if (B < 1 || H < 1 || N < 1) return FA_ERR_BAD_SHAPE;
+    int err = 0;
+    DeviceState* st = device_state(&err);
+    if (!st) return err;
+    const size_t bytes = (size_t)B * H * N * D * sizeof(__half);
+    std::lock_guard<std::mutex> lock(st->host_mu);
+    cudaError_t e;
+    if (!st->host_stream) {
+        if ((e = cudaStreamCreateWithFlags(&st->host_stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+    }
+    if (st->stage_bytes < 4 * bytes) {
+        if (st->stage) cudaFree(st->stage);
+        st->stage = nullptr;
+        st->stage_bytes = 0;
+        if ((e = cudaMalloc(&st->stage, 4 * bytes)) != cudaSuccess) return (int)e;
+        st->stage_bytes = 4 * bytes;
+    }
+    char* base = static_cast<char*>(st->stage);
+    void *dq = base, *dk = base + bytes, *dv = base + 2 * bytes, *dout = base + 3 * bytes;
+    cudaStream_t s = st->host_stream;
+    // FA.cu:774-776
+    if ((e = cudaMemcpyAsync(dq, hq, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpyAsync(dk, hk, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpyAsync(dv, hv, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+    int rc = flash_attn_fwd(dq, dk, dv, dout, B, H, N, D, causal, s);   // FA.cu:777
+    if (rc != FA_OK) return rc;
+    // FA.cu:779-780
+    if ((e = cudaMemcpyAsync(ho, dout, bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize(s);
+}
+
+int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_attn_kernel_info* info) {
+    (void)causal;
+    if (!info) return FA_ERR_NULL_PTR;
+    if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+    if (B < 1 || H < 1 || N < 1) return FA_ERR_BAD_SHAPE;
+    memset(info, 0, sizeof *info);
+    cudaFuncAttributes attr;
+    cudaError_t e = D == 128 ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128>)
+                             : cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<64>);
+    if (e != cudaSuccess) return (int)e;
+    int err = 0;
+    DeviceState* st = device_state(&err);
+    if (!st) return err;
+    fa::Params p = make_params(B * H, N, N, D, causal, 0);
+    info->regs_per_thread = attr.numRegs;
+    info->local_bytes_per_thread = (int)attr.localSizeBytes;
+    info->static_smem_bytes = (int)attr.sharedSizeBytes;
+    info->dynamic_smem_bytes = D == 128 ? fa::Cfg<128>::kSmemBytes : fa::Cfg<64>::kSmemBytes;
+    info->threads_per_cta = fa::kNumThreads;
+    info->ctas = p.total_work < st->num_sms ? p.total_work : st->num_sms;
+    info->tmem_columns = fa::kTmemCols;
+    info->kv_stages = D == 128 ? fa::Cfg<128>::kStages : fa::Cfg<64>::kStages;
+    info->work_items = p.total_work;
+    info->num_sms = st->num_sms;
+    return FA_OK;
+}
+
+unsigned long long flash_attn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void flash_attn_destroy(void) {
+    int saved = 0;
+    if (cudaGetDevice(&saved) != cudaSuccess) return;
+    for (int d = 0; d < kMaxDevices; d++) {
+        DeviceState* st = &g_dev[d];
+        std::lock_guard<std::mutex> lock(st->host_mu);
+        if (st->stage || st->host_stream) {
+            cudaSetDevice(d);
+            if (st->stage) cudaFree(st->stage);
+            if (st->host_stream) cudaStreamDestroy(st->host_stream);
+            st->stage = nullptr;
+            st->stage_bytes = 0;
+            st->host_stream = nullptr;
+        }
+    }
+    cudaSetDevice(saved);
+}
+
+const char* flash_attn_error_string(int code) {
+    switch (code) {
+        case FA_OK: return "success";
+        case FA_ERR_BAD_HEAD_DIM: return "head_dim must be 64 or 128";
+        case FA_ERR_NULL_PTR: return "null pointer argument";
+        case FA_ERR_MISALIGNED: return "tensor base pointers must be 16-byte aligned";
+        case FA_ERR_BAD_SHAPE: return "invalid shape (B, H, N must be >= 1 and within tensor-map limits)";
+        case FA_ERR_UNSUPPORTED_ARCH: return "device is not compute capability 10.x (B200, sm_100a)";
+        case FA_ERR_TENSORMAP: return "cuTensorMapEncodeTiled failed or is unavailable";
+        case FA_ERR_WORKSPACE: return "workspace missing or too small";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+const char* flash_attn_version(void) { return "flashattn_b200 0.1 (sm_100a tcgen05/TMA forward)"; }
+
+}  // extern "C"
+
+// Host-side mirror of the device work decomposition, exported for the scheduler tests
+// (every (bh, q-tile) exactly once, heavy-first, masked tiles skipped).
+extern "C" int flash_attn_debug_work_item(int w, int B, int H, int Nq, int Nkv, int D, int causal, long long shift,
+                                          int* total, int* bh, int* q0, int* n0, int* n1) {
+    if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+    fa::Params p = make_params(B * H, Nq, Nkv, D, causal, shift);
+    *total = p.total_work;
+    if (w < 0 || w >= p.total_work) return FA_ERR_BAD_SHAPE;
+    fa::WorkItem it = fa::decode_work(w, p);
+    *bh = it.bh; *q0 = it.q0; *n0 = it.n0; *n1 = it.n1;
+    return FA_OK;
+}

@@ -1,0 +1,510 @@
+// fa_fwd_sm100.cuh -- FlashAttention forward for B200 (sm_100a): persistent, warp-specialised,
+// TMA -> 128B-swizzled smem -> tcgen05.mma with S/P/O in tensor memory.
+//
+// Replaces the reference's device path flash_attention_v9<...> (flash_attention.cu:67-554):
+//   FA.cu:103-112  block->(bh, q-block) mapping, GRID_SWAP    -> persistent work loop, heavy-first
+//   FA.cu:145-159  Q fragments in registers                   -> Q tile pair resident in smem (TMA)
+//   FA.cu:417-447  synchronous K/V tile load + 2 barriers     -> producer warp, mbarrier ring
+//   FA.cu:188-233  DO_QK_MATMUL (mma.sync m16n8k16)           -> tcgen05.mma SS, S in TMEM
+//   FA.cu:235-288  DO_SOFTMAX (quad shuffles, eager rescale)  -> one thread per row, lazy rescale
+//   FA.cu:290-334  DO_PV_MATMUL (P in registers)              -> P fp16 in TMEM, tcgen05.mma TS
+//   FA.cu:497-553  epilogue via smem                          -> TMEM -> registers -> global
+//   FA.cu:460-496  split-K partial epilogue (dead code there) -> partial mode used by ring CP
+//
+// CTA = 384 threads:  warps 0-3  softmax/correction/epilogue for Q tile 0 (128 rows)
+//                     warps 4-7  same for Q tile 1
+//                     warp 8     TMEM allocator + tcgen05.mma issuer (one lane)
+//                     warp 9     TMA producer (one lane)
+//                     warps 10,11 idle (pad the third warpgroup)
+// One CTA per SM; each CTA loops over work items (bh, pair of 128-row Q tiles).
+//
+// TMEM (512 columns x 128 lanes x 32 bit): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).
+// P_t (fp16, two per column) overwrites columns [0,64) of S_t once the owning thread has read
+// its S row.  Tensor-pipe order per KV tile j:  PV0(j) QK0(j+1) PV1(j) QK1(j+1), so each softmax
+// warpgroup works on S_t(j+1) while the tensor core runs the other tile's two MMAs.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "sm100_ptx.cuh"
+
+namespace fa {
+
+using namespace sm100;
+
+constexpr int kBlockM = 128;      // Q rows per tile  (UMMA M)
+constexpr int kBlockN = 128;      // K/V rows per tile (UMMA N of QK^T, K extent of PV)
+constexpr int kNumThreads = 384;
+constexpr int kMmaWarp = 8;
+constexpr int kLoadWarp = 9;
+constexpr int kTmemCols = 512;
+constexpr float kRescaleThreshold = 8.0f;  // lazy rescale: tolerate P up to 2^8 before moving the reference max
+
+template <int D>
+struct Cfg {
+    static_assert(D == 64 || D == 128, "head_dim must be 64 or 128");
+    static constexpr int kPanels = D / 64;                 // 128-byte swizzle panels per row
+    static constexpr int kPanelBytes = 128 * 128;          // 128 rows x 128 B
+    static constexpr int kTileBytes = kPanels * kPanelBytes;
+    static constexpr int kStages = (D == 128) ? 5 : 8;     // K/V ring entries (one tile each)
+    static constexpr int kSmemQ = 2 * kTileBytes;
+    static constexpr int kSmemKV = kStages * kTileBytes;
+    static constexpr int kBarOffset = kSmemQ + kSmemKV;
+    static constexpr int kNumBars = 2 + 2 * kStages + 6;
+    static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 16 + 1024;  // +1024: manual alignment slack
+    static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
+    static constexpr uint32_t kIdescQK = umma_idesc_f16(kBlockM, kBlockN, 0, 0);
+    static constexpr uint32_t kIdescPV = umma_idesc_f16(kBlockM, D, 0, 1);  // V is MN-major ([kv][d], d contiguous)
+};
+
+struct Params {
+    __half* o;          // fp16 output [BH, Nq, D]            (partial_mode == 0)
+    float* o_partial;   // fp32 un-normalised [BH*Nq, D]       (partial_mode == 1; FA.cu:460-496 format)
+    float* ml;          // (m, l) pairs [BH*Nq, 2]
+    int Nq, Nkv, BH;
+    int causal;
+    int shift;          // q_offset - kv_offset: key c visible to query r iff c <= r + shift
+    int nqp;            // Q tile pairs per head = ceil(Nq / 256)
+    int total_work;     // BH * nqp
+    int partial_mode;
+    int accumulate;
+    float scale;        // 1/sqrt(D)
+    float scale_log2;   // scale * log2(e)
+};
+
+// ---- work decomposition (shared by host tests and every warp role) ----
+struct WorkItem {
+    int bh, q0;      // head index, first local query row of the pair
+    int n0, n1;      // KV tiles the two Q tiles need (0 = nothing visible / tile absent)
+};
+__host__ __device__ inline int kv_trip_count(int q_start, int Nq, int Nkv, int causal, int shift) {
+    if (q_start >= Nq) return 0;
+    const int nkv_tiles = (Nkv + kBlockN - 1) / kBlockN;
+    if (!causal) return nkv_tiles;
+    int last_row = q_start + kBlockM - 1;
+    if (last_row > Nq - 1) last_row = Nq - 1;
+    long long vis = (long long)last_row + shift + 1;  // keys [0, vis) visible to the last row
+    if (vis <= 0) return 0;
+    if (vis > Nkv) vis = Nkv;
+    return (int)((vis + kBlockN - 1) / kBlockN);
+}
+// Work order: heads outermost (the CTAs running concurrently share a few heads' K/V in L2),
+// heaviest Q pair first inside a head (causal: the last pair sees the most keys).
+__host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
+    WorkItem it;
+    it.bh = w / p.nqp;
+    const int qp = p.nqp - 1 - (w % p.nqp);
+    it.q0 = qp * 2 * kBlockM;
+    it.n0 = kv_trip_count(it.q0, p.Nq, p.Nkv, p.causal, p.shift);
+    it.n1 = kv_trip_count(it.q0 + kBlockM, p.Nq, p.Nkv, p.causal, p.shift);
+    return it;
+}
+
+struct Ring {
+    uint32_t idx, phase;
+    template <int kStages>
+    __device__ __forceinline__ void advance() {
+        if (++idx == (uint32_t)kStages) { idx = 0; phase ^= 1u; }
+    }
+};
+
+// ---- softmax of one 128x128 S tile; one thread owns one row ----
+template <int D, bool kMask>
+__device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
+                                             uint32_t bar_o_full, int lim_local, bool have_o,
+                                             uint32_t pv_count, float& m_ref, float& l_run) {
+    uint32_t s[kBlockN];
+    tmem_ld_x32(tS + 0, s + 0);
+    tmem_ld_x32(tS + 32, s + 32);
+    tmem_ld_x32(tS + 64, s + 64);
+    tmem_ld_x32(tS + 96, s + 96);
+    tmem_wait_ld();
+
+    if (kMask) {
+#pragma unroll
+        for (int i = 0; i < kBlockN; i++)
+            if (i >= lim_local) s[i] = 0xff800000u;  // -inf
+    }
+
+    float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+    float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+#pragma unroll
+    for (int i = 4; i < kBlockN; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[i + 0]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+    }
+    const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    const float m_new = fmaxf(m_ref, m_tile);
+
+    // Lazy rescale (replaces the reference's every-tile O *= alpha, FA.cu:267-270): the reference
+    // max only moves when the true max has outgrown it by 2^kRescaleThreshold.
+    const bool need = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;  // NaN (-inf - -inf) -> false
+    if (__any_sync(0xffffffffu, need)) {
+        if (have_o) {
+            const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
+            // O_t holds PV(0..j-1); the last of them must have retired before we touch it
+            mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 40);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < D; c += 32) {
+                uint32_t o[32];
+                tmem_ld_x32(tO + c, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_x32(tO + c, o);
+            }
+            l_run *= alpha;
+        }
+        m_ref = m_new;
+    }
+
+    const float m_used = (m_ref == -INFINITY) ? 0.0f : m_ref;
+    const float neg = -m_used * p.scale_log2;
+    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+    uint32_t pk[kBlockN / 2];
+#pragma unroll
+    for (int i = 0; i < kBlockN; i += 4) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(s[i + 0]), p.scale_log2, neg));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), p.scale_log2, neg));
+        const float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), p.scale_log2, neg));
+        sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;   // row sum of the un-rounded p (FA.cu:273-279)
+        __half2 h01 = __floats2half2_rn(p0, p1);           // low half = even column
+        __half2 h23 = __floats2half2_rn(p2, p3);
+        pk[i / 2 + 0] = *reinterpret_cast<uint32_t*>(&h01);
+        pk[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h23);
+    }
+    // P_t (fp16 A operand of PV) overwrites columns [0,64) of S_t
+    tmem_st_x32(tS + 0, pk + 0);
+    tmem_st_x32(tS + 32, pk + 32);
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(bar_p_full);
+    l_run += (sum0 + sum1) + (sum2 + sum3);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kNumThreads, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, const Params p) {
+    using C = Cfg<D>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = smem_base;
+    const uint32_t sKV = smem_base + C::kSmemQ;
+    const uint32_t bars = smem_base + C::kBarOffset;
+    const uint32_t bar_q_full = bars + 0;
+    const uint32_t bar_q_empty = bars + 8;
+    const uint32_t bar_kv_full = bars + 16;                       // [kStages]
+    const uint32_t bar_kv_empty = bar_kv_full + 8 * C::kStages;   // [kStages]
+    const uint32_t bar_s_full = bar_kv_empty + 8 * C::kStages;    // [2]
+    const uint32_t bar_p_full = bar_s_full + 16;                  // [2]
+    const uint32_t bar_o_full = bar_p_full + 16;                  // [2]
+    const uint32_t tmem_slot = bar_o_full + 16;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_q_full, 1);
+        mbar_init(bar_q_empty, 1);
+        for (int i = 0; i < C::kStages; i++) {
+            mbar_init(bar_kv_full + 8 * i, 1);
+            mbar_init(bar_kv_empty + 8 * i, 1);
+        }
+        for (int t = 0; t < 2; t++) {
+            mbar_init(bar_s_full + 8 * t, 1);
+            mbar_init(bar_p_full + 8 * t, kBlockM);   // every softmax thread of the tile arrives
+            mbar_init(bar_o_full + 8 * t, 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == kMmaWarp) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    if (warp == kLoadWarp && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == kLoadWarp) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            Ring ring{0u, 0u};
+            uint32_t it = 0;
+            for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+                const WorkItem wi = decode_work(w, p);
+                const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
+                const bool have_q1 = wi.q0 + kBlockM < p.Nq;
+                mbar_wait(bar_q_empty, (it & 1u) ^ 1u, 1);   // previous item's QK^T MMAs retired
+                mbar_arrive_expect_tx(bar_q_full, (have_q1 ? 2 : 1) * C::kTileBytes);
+                for (int t = 0; t < (have_q1 ? 2 : 1); t++)
+                    for (int pn = 0; pn < C::kPanels; pn++)
+                        tma_load_3d(sQ + t * C::kTileBytes + pn * C::kPanelBytes, &tmQ, bar_q_full, pn * 64,
+                                    wi.q0 + t * kBlockM, wi.bh);
+                for (int j = 0; j < nmax; j++) {
+                    // ring order K_0 V_0 K_1 V_1 ... (the order the MMA warp releases them in)
+                    for (int kv = 0; kv < 2; kv++) {
+                        const uint32_t full = bar_kv_full + 8 * ring.idx;
+                        mbar_wait(bar_kv_empty + 8 * ring.idx, ring.phase ^ 1u, 2);
+                        mbar_arrive_expect_tx(full, C::kTileBytes);
+                        const uint32_t dst = sKV + ring.idx * C::kTileBytes;
+                        for (int pn = 0; pn < C::kPanels; pn++)
+                            tma_load_3d(dst + pn * C::kPanelBytes, kv == 0 ? &tmK : &tmV, full, pn * 64,
+                                        j * kBlockN, wi.bh);
+                        ring.advance<C::kStages>();
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // =============================== tcgen05.mma issuer ===============================
+        if (lane == 0) {
+            Ring rk{0u, 0u};              // ring entry holding K_j
+            Ring rv{1u % C::kStages, 0u}; // ring entry holding V_j
+            uint32_t it = 0;
+            uint32_t p_phase[2] = {0u, 0u};
+            const uint32_t tS[2] = {tmem_base + C::kTmemS0, tmem_base + C::kTmemS1};
+            const uint32_t tO[2] = {tmem_base + C::kTmemO0, tmem_base + C::kTmemO1};
+
+            // S_t = Q_t K_j^T : D/16 k-steps; k-step ks lives in panel ks/4 at byte offset (ks%4)*32
+            auto issue_qk = [&](int t, uint32_t k_smem) {
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ks++) {
+                    const uint32_t off = (ks >> 2) * C::kPanelBytes + (ks & 3) * 32;
+                    const uint64_t ad = umma_smem_desc(sQ + t * C::kTileBytes + off, 16, 1024);
+                    const uint64_t bd = umma_smem_desc(k_smem + off, 16, 1024);
+                    umma_ss(tS[t], ad, bd, C::kIdescQK, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(bar_s_full + 8 * t);
+            };
+            // O_t (+)= P_t V_j : 8 k-steps of 16 kv rows; P k-step = 8 TMEM columns, V k-step = 16 rows * 128 B
+            auto issue_pv = [&](int t, uint32_t v_smem, bool accumulate) {
+#pragma unroll
+                for (int ks = 0; ks < kBlockN / 16; ks++) {
+                    const uint64_t bd = umma_smem_desc(v_smem + ks * 16 * 128, C::kPanelBytes, 1024);
+                    umma_ts(tO[t], tS[t] + ks * 8, bd, C::kIdescPV, (accumulate || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(bar_o_full + 8 * t);
+            };
+
+            for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+                const WorkItem wi = decode_work(w, p);
+                const int n[2] = {wi.n0, wi.n1};
+                const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
+                mbar_wait(bar_q_full, it & 1u, 10);
+                tc_fence_after();
+                if (nmax > 0) {
+                    mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 11);
+                    tc_fence_after();
+                    const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
+                    if (n[0] > 0) issue_qk(0, k_smem);
+                    if (n[1] > 0) issue_qk(1, k_smem);
+                    umma_commit(bar_kv_empty + 8 * rk.idx);
+                    rk.advance<C::kStages>(); rk.advance<C::kStages>();
+                }
+                // Q is free for the next item as soon as the last QK^T of this one has retired
+                if (nmax <= 1) umma_commit(bar_q_empty);
+                for (int j = 0; j < nmax; j++) {
+                    const bool has_next = j + 1 < nmax;
+                    mbar_wait(bar_kv_full + 8 * rv.idx, rv.phase, 12);
+                    const uint32_t v_smem = sKV + rv.idx * C::kTileBytes;
+                    const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        if (j < n[t]) {
+                            mbar_wait(bar_p_full + 8 * t, p_phase[t], 13 + t);
+                            p_phase[t] ^= 1u;
+                            tc_fence_after();
+                            issue_pv(t, v_smem, j > 0);
+                        }
+                        if (t == 0 && has_next) {
+                            mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 15);
+                            tc_fence_after();
+                        }
+                        if (t == 1) {
+                            umma_commit(bar_kv_empty + 8 * rv.idx);
+                            rv.advance<C::kStages>(); rv.advance<C::kStages>();
+                        }
+                        if (j + 1 < n[t]) issue_qk(t, k_smem);
+                    }
+                    if (has_next) {
+                        umma_commit(bar_kv_empty + 8 * rk.idx);
+                        rk.advance<C::kStages>(); rk.advance<C::kStages>();
+                        if (j + 2 == nmax) umma_commit(bar_q_empty);   // QK^T(nmax-1) was the last reader of Q
+                    }
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // =============================== softmax / correction / epilogue ===============================
+        const int t = warp >> 2;                               // which Q tile of the pair
+        const int row_in_tile = (warp & 3) * 32 + lane;        // TMEM lane == S/O row
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem_base + lane_base + (t ? C::kTmemS1 : C::kTmemS0);
+        const uint32_t tO = tmem_base + lane_base + (t ? C::kTmemO1 : C::kTmemO0);
+        const uint32_t my_s_full = bar_s_full + 8 * t;
+        const uint32_t my_p_full = bar_p_full + 8 * t;
+        const uint32_t my_o_full = bar_o_full + 8 * t;
+        uint32_t s_phase = 0;
+        uint32_t pv_count = 0;   // P tiles handed to the MMA warp so far == o_full completions expected
+
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+            const WorkItem wi = decode_work(w, p);
+            const int q_start = wi.q0 + t * kBlockM;
+            if (q_start >= p.Nq) continue;                     // this Q tile does not exist
+            const int n_t = t ? wi.n1 : wi.n0;
+            const int row = q_start + row_in_tile;             // local query row
+            // keys [0, lim) are visible to this row
+            long long lim_ll = p.causal ? (long long)row + p.shift + 1 : (long long)p.Nkv;
+            if (lim_ll > p.Nkv) lim_ll = p.Nkv;
+            if (lim_ll < 0) lim_ll = 0;
+            const int lim = (int)lim_ll;
+
+            float m_ref = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < n_t; j++) {
+                mbar_wait(my_s_full, s_phase, 20 + t);
+                s_phase ^= 1u;
+                tc_fence_after();
+                const int k0 = j * kBlockN;
+                const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
+                if (need_mask)
+                    softmax_tile<D, true>(p, tS, tO, my_p_full, my_o_full, lim - k0, j > 0, pv_count, m_ref, l_run);
+                else
+                    softmax_tile<D, false>(p, tS, tO, my_p_full, my_o_full, kBlockN, j > 0, pv_count, m_ref, l_run);
+                ++pv_count;
+            }
+
+            // ---- epilogue: O_t / l -> fp16 -> global (or the partial-state format) ----
+            if (n_t > 0) {
+                mbar_wait(my_o_full, (pv_count - 1u) & 1u, 30 + t);
+                tc_fence_after();
+            }
+            const bool row_ok = row < p.Nq;
+            const size_t grow = (size_t)wi.bh * p.Nq + row;
+            if (!p.partial_mode) {
+                const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;   // FA.cu:502-503
+                __half* orow = p.o + grow * D;
+#pragma unroll
+                for (int c = 0; c < D; c += 32) {
+                    uint32_t o[32];
+                    if (n_t > 0) {
+                        tmem_ld_x32(tO + c, o);
+                        tmem_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) o[i] = 0u;
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 v;
+                            __half2 h;
+                            h = __floats2half2_rn(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
+                            v.x = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2half2_rn(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                            v.y = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2half2_rn(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                            v.z = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2half2_rn(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+                            v.w = *reinterpret_cast<uint32_t*>(&h);
+                            *reinterpret_cast<uint4*>(orow + c + i) = v;
+                        }
+                    }
+                }
+            } else {
+                // partial state (FA.cu:460-496): un-normalised fp32 O, (m, l) with m in the
+                // scaled-score (natural-log) domain; merge algebra of FA.cu:575-597 when accumulating
+                float m_out = (m_ref == -INFINITY) ? -FLT_MAX : m_ref * p.scale;
+                float l_out = l_run;
+                float w_new = 1.f, w_old = 0.f;
+                float* prow = p.o_partial + grow * D;
+                if (p.accumulate && row_ok) {
+                    const float m_old = p.ml[grow * 2 + 0];
+                    const float l_old = p.ml[grow * 2 + 1];
+                    const float m_max = fmaxf(m_old, m_out);
+                    const float kLog2e = 1.4426950408889634f;
+                    w_old = (m_old <= -FLT_MAX) ? 0.f : ex2_approx((m_old - m_max) * kLog2e);
+                    w_new = (m_out <= -FLT_MAX) ? 0.f : ex2_approx((m_out - m_max) * kLog2e);
+                    l_out = l_old * w_old + l_run * w_new;
+                    m_out = m_max;
+                }
+#pragma unroll
+                for (int c = 0; c < D; c += 32) {
+                    uint32_t o[32];
+                    if (n_t > 0) {
+                        tmem_ld_x32(tO + c, o);
+                        tmem_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) o[i] = 0u;
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 v = make_float4(__uint_as_float(o[i]) * w_new, __uint_as_float(o[i + 1]) * w_new,
+                                                   __uint_as_float(o[i + 2]) * w_new, __uint_as_float(o[i + 3]) * w_new);
+                            if (p.accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(prow + c + i);
+                                v.x += old.x * w_old; v.y += old.y * w_old;
+                                v.z += old.z * w_old; v.w += old.w * w_old;
+                            }
+                            *reinterpret_cast<float4*>(prow + c + i) = v;
+                        }
+                    }
+                }
+                if (row_ok) {
+                    p.ml[grow * 2 + 0] = m_out;
+                    p.ml[grow * 2 + 1] = l_out;
+                }
+            }
+            // O_t / S_t are free again: the next item's first P arrival orders after these reads
+            tc_fence_before();
+        }
+    }
+
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// fp16 O = o_partial / l  (final step of the FA.cu:575-597 merge)
+__global__ void fa_finalize_kernel(const float* __restrict__ o_partial, const float* __restrict__ ml,
+                                   __half* __restrict__ o, long long rows, int D) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
+    const int per_row = D / 4;
+    const long long r = idx / per_row;
+    if (r >= rows) return;
+    const int c = (int)(idx % per_row) * 4;
+    const float l = ml[r * 2 + 1];
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    const float4 v = *reinterpret_cast<const float4*>(o_partial + r * D + c);
+    __half2 a = __floats2half2_rn(v.x * inv, v.y * inv);
+    __half2 b = __floats2half2_rn(v.z * inv, v.w * inv);
+    uint2 out;
+    out.x = *reinterpret_cast<uint32_t*>(&a);
+    out.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(o + r * D + c) = out;
+}
+
+}  // namespace fa

@@ -1,0 +1,239 @@
+// sm100_ptx.cuh -- thin inline-PTX layer for Blackwell (sm_100a): mbarrier, TMA, tcgen05
+// (TMEM alloc / ld / st / mma / commit) and UMMA descriptor encoders.
+//
+// Everything here is a 1:1 wrapper over one PTX instruction, so the kernels read as the
+// hardware protocol they implement.  Compile with -gencode arch=compute_100a,code=sm_100a.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace sm100 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t lane_id() {
+    uint32_t l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
+}
+
+// ------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Blocking wait with a watchdog: a protocol bug shows up as a trapped kernel with the
+// barrier's tag printed, not as a hung GPU.  ~2^32 cycles is >1.5 s; no legitimate wait in
+// these kernels is longer than a few milliseconds.
+__device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
+    printf("[fa_sm100] mbarrier wait timed out: block %d thread %d tag %d parity %u\n",
+           (int)blockIdx.x, (int)threadIdx.x, tag, parity);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++polls & 63u) == 0u && clock64() - t0 > (1ll << 32)) mbar_timeout(tag, parity);
+    }
+}
+
+// ------------------------------------------------------------------ proxies / fences
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ TMA (cp.async.bulk.tensor)
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, uint32_t bar,
+                                            int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst_smem, const void* tmap, uint32_t bar,
+                                                 int c0, int c1, int c2, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar),
+        "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src_smem, int c0, int c1,
+                                             int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
+// ------------------------------------------------------------------ TMEM allocation
+// One full warp executes alloc/dealloc (.sync.aligned).  The base address is written to smem.
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+
+// ------------------------------------------------------------------ tcgen05.mma / commit
+// D[tmem] (+)= A[smem desc] * B[smem desc]; one thread issues for the CTA.
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                        uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                        uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive (count 1) on an mbarrier once every tcgen05.mma issued so far by this thread has
+// completed.  Implies tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+
+// ------------------------------------------------------------------ tcgen05.ld / st (32 lanes x 32b, xN columns)
+// Thread `lane` of warp w touches TMEM lane 32*(w%4)+lane and N consecutive 32-bit columns.
+#define FA_R4(a, i) a[i], a[i + 1], a[i + 2], a[i + 3]
+#define FA_OUT4(a, i) "=r"(a[i]), "=r"(a[i + 1]), "=r"(a[i + 2]), "=r"(a[i + 3])
+#define FA_IN4(a, i) "r"(a[i]), "r"(a[i + 1]), "r"(a[i + 2]), "r"(a[i + 3])
+
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : FA_OUT4(r, 0), FA_OUT4(r, 4), FA_OUT4(r, 8), FA_OUT4(r, 12), FA_OUT4(r, 16),
+          FA_OUT4(r, 20), FA_OUT4(r, 24), FA_OUT4(r, 28)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : FA_OUT4(r, 0), FA_OUT4(r, 4), FA_OUT4(r, 8), FA_OUT4(r, 12)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), FA_IN4(r, 0), FA_IN4(r, 4), FA_IN4(r, 8), FA_IN4(r, 12), FA_IN4(r, 16),
+        FA_IN4(r, 20), FA_IN4(r, 24), FA_IN4(r, 28)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), FA_IN4(r, 0), FA_IN4(r, 4), FA_IN4(r, 8), FA_IN4(r, 12)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ UMMA descriptors
+// Shared-memory matrix descriptor (64 bit), SWIZZLE_128B, Blackwell version field = 1.
+//   [0,14)  start address >> 4      [16,30) leading byte offset >> 4
+//   [32,46) stride byte offset >> 4 [46,48) version = 1   [61,64) layout type (2 = 128B swizzle)
+// K-major operand (rows x 64 halves panels, 128 B per row): SBO = 8 rows * 128 B = 1024,
+// LBO unused (1).  MN-major operand (K rows x 64 halves panels): SBO = 1024 between groups of
+// 8 K-rows, LBO = byte distance between successive 64-element MN chunks (the panel stride).
+__host__ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                            uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+// Instruction descriptor (32 bit) for kind::f16 with fp16 A/B and fp32 accumulate.
+//   [4,6) D format (1 = f32)  [7,10) A format (0 = f16)  [10,13) B format (0 = f16)
+//   [15] A major (0 = K)      [16] B major (0 = K, 1 = MN)
+//   [17,23) N >> 3            [24,29) M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (static_cast<uint32_t>(a_mn_major) << 15) |
+           (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ math
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+}  // namespace sm100

@@ -1,0 +1,115 @@
+/*
+ * flash_attn.h -- C ABI of libflashattn_b200.so: FlashAttention forward for NVIDIA B200 (sm_100a).
+ *
+ * Drop-in boundary for the reference's host launcher
+ *     void flash_attention_v9_dispatch(const half* Q, const half* K, const half* V, half* Output,
+ *                                      float* splitk_buf_O, float* splitk_buf_ml,
+ *                                      int batch_size, int num_heads, int seq_len, int head_dim,
+ *                                      bool causal, cudaStream_t stream = 0)
+ * (reference flash_attention.cu:606-663).  Same data contract:
+ *   - device pointers, FP16, contiguous [B, H, N, D] (row stride D, head stride N*D; FA.cu:119-122)
+ *   - softmax scale fixed to 1/sqrt(D) (FA.cu:612)
+ *   - causal = lower-triangular including the diagonal: query i sees keys 0..i (FA.cu:250-255, 679)
+ *   - O is fully overwritten for rows < N; caller owns every buffer; the call only enqueues work on
+ *     `stream` and returns (FA.cu:634-662)
+ * Differences, all widening: D may be 64 or 128 (the reference hard-codes 128, FA.cu:613), 64-bit
+ * indexing (the reference indexes with int, FA.cu:119-122), errors are returned instead of
+ * exit(EXIT_FAILURE) (FA.cu:22-30).  Plain pointers and sizes only; `stream` is a cudaStream_t
+ * passed as void* so the header needs no CUDA include.
+ */
+#ifndef FLASH_ATTN_B200_H
+#define FLASH_ATTN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Return codes: 0 = success; > 0 = a cudaError_t from the runtime; < 0 = argument errors below. */
+#define FA_OK 0
+#define FA_ERR_BAD_HEAD_DIM (-1) /* D not in {64, 128} */
+#define FA_ERR_NULL_PTR (-2)
+#define FA_ERR_MISALIGNED (-3) /* base pointer not 16-byte aligned (TMA global-address rule) */
+#define FA_ERR_BAD_SHAPE (-4)  /* B, H or N < 1, or B*H / N beyond the tensor-map limits */
+#define FA_ERR_UNSUPPORTED_ARCH (-5) /* current device is not compute capability 10.x */
+#define FA_ERR_TENSORMAP (-6)        /* cuTensorMapEncodeTiled failed */
+#define FA_ERR_WORKSPACE (-7)        /* workspace too small / missing for an _ex call */
+
+/* Replaces flash_attention_v9_dispatch (FA.cu:606-663).  Argument order is the one the
+ * north-star names: q, k, v, o, B, H, N, D, causal, stream. */
+int flash_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int H, int N, int D,
+                   int causal, void* stream);
+
+/* Extended entry: one K/V block of a longer sequence, for ring context
+ * parallelism and split-KV.  Computes attention of the local queries q[B,H,Nq,D] against
+ * k/v[B,H,Nkv,D] where the queries sit at global positions q_offset.. and the keys at
+ * kv_offset.. (the causal mask compares global positions), and emits the reference's split-K
+ * partial format (FA.cu:460-496): o_partial fp32 un-normalised [B*H*Nq, D] and ml [B*H*Nq, 2] =
+ * (row max in the scaled-score domain, row sum).  When `accumulate` is non-zero the partials
+ * already in o_partial/ml are merged in with the algebra of FA.cu:575-597, so a ring of P hops
+ * is P calls on the same buffers.  flash_attn_finalize() then writes O = o_partial / l as FP16. */
+int flash_attn_fwd_ex(const void* q, const void* k, const void* v, float* o_partial, float* ml,
+                      int B, int H, int Nq, int Nkv, int D, int causal, long long q_offset,
+                      long long kv_offset, int accumulate, void* stream);
+int flash_attn_finalize(const float* o_partial, const float* ml, void* o, long long rows, int D,
+                        void* stream);
+
+/* The reference harness's call pattern with HOST buffers (FA.cu:771-780): H2D of Q,K,V,
+ * dispatch, D2H of O, on a per-device cached staging workspace.  Blocks until O is on the host. */
+int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho, int B, int H, int N,
+                        int D, int causal);
+
+/* Resource report of the kernel flash_attn_fwd would launch for this shape (the reference prints
+ * regs/spill/occupancy for its instantiations, FA.cu:711-755). */
+typedef struct {
+    int regs_per_thread;
+    int local_bytes_per_thread; /* spills */
+    int static_smem_bytes;
+    int dynamic_smem_bytes;
+    int threads_per_cta;
+    int ctas; /* persistent grid size */
+    int tmem_columns;
+    int kv_stages;
+    int work_items; /* (b,h,q-tile-pair) units the grid loops over */
+    int num_sms;
+} flash_attn_kernel_info;
+int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_attn_kernel_info* info);
+
+/* Number of kernels this library has launched in the calling process (all threads). */
+unsigned long long flash_attn_launch_count(void);
+
+/* Frees the per-device caches (staging buffers of flash_attn_fwd_host). */
+void flash_attn_destroy(void);
+
+const char* flash_attn_error_string(int code);
+const char* flash_attn_version(void);
+
+#ifdef __cplusplus
+} /* extern "C" */
+
+/* C++ shim with the reference's exact 12-argument signature and error behaviour (print
+ * file:line-style message, exit(EXIT_FAILURE); FA.cu:22-30, 606-611).  The split-K buffers are
+ * accepted and ignored, as in the reference (never dereferenced there, FA.cu:634-660). */
+#if defined(__CUDACC__) || defined(FLASH_ATTN_WITH_CUDA_TYPES)
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+static inline void flash_attention_b200_dispatch(const half* Q, const half* K, const half* V,
+                                                 half* Output, float* /*splitk_buf_O*/,
+                                                 float* /*splitk_buf_ml*/, int batch_size,
+                                                 int num_heads, int seq_len, int head_dim,
+                                                 bool causal, cudaStream_t stream = 0) {
+    int rc = flash_attn_fwd(Q, K, V, Output, batch_size, num_heads, seq_len, head_dim, causal ? 1 : 0,
+                            (void*)stream);
+    if (rc != FA_OK) {
+        fprintf(stderr, "flash_attn_fwd: %s (%d)\n", flash_attn_error_string(rc), rc);
+        exit(EXIT_FAILURE);
+    }
+}
+#endif
+#endif
+
+#endif /* FLASH_ATTN_B200_H */
