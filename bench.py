@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path: FlashAttention forward, FP16, on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cpu]
+                    [--workload NAME] [--sweep]
+
+One "step" = one forward pass over one synthetic batch of the named workload (default: the shape
+BASELINE.json's metric is quoted on -- B=1 H=32 D=128 seq=8192 causal, the README table's shape at
+the north-star target length).  Prints ONE JSON line (rank 0):
+
+  value     whole-job forward TFLOPS (FLOPs = 4*B*H*N^2*D, /2 causal -- the reference's convention,
+            flash_attention.cu:938-939), inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       the same metric through the C-ABI call with HOST buffers (flash_attn_fwd_host: H2D of
+            Q,K,V from pinned memory + kernel + D2H of O inside the timed region)
+  roofline  tensor-bound: achieved TFLOPS of the kernel vs the measured cuBLAS bf16 peak
+  cpu_baseline  the CPU oracle (port of the reference's cpu_attention) on a bounded row sample
+
+`--impl reference` runs the UNMODIFIED reference kernel (V9, flash_attention_v9_dispatch) rebuilt for
+sm_100a from /root/reference into oracle/_ref/libref_v9.so, on the same workload with the same timing
+code.  The reference's implementation of this path is a GPU kernel, so that is what the reference arm
+times; its CPU check function (cpu_attention) is reported beside it as `cpu_baseline`
+(`--impl reference-cpu` times only that).  Multi-GPU: every rank runs the workload on its own GPU
+(batch x heads shard, no collective on the data path) -> "scaling": "weak".
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+WORKLOADS = {
+    # name: (B, H, N, D, causal)
+    "cfg1_n1024_causal": (1, 32, 1024, 128, 1),          # BASELINE.json configs[0]
+    "cfg2_n8192_causal": (1, 32, 8192, 128, 1),          # configs[1], headline
+    "cfg2_n8192_full": (1, 32, 8192, 128, 0),
+    "cfg2_n16384_causal": (1, 32, 16384, 128, 1),
+    "cfg2_n16384_full": (1, 32, 16384, 128, 0),
+    "cfg3_b16_n8192_causal": (16, 32, 8192, 128, 1),     # configs[2] (strong scaling: B*H sharded)
+    "cfg4_d64_n2048_full": (32, 16, 2048, 64, 0),        # configs[3]
+}
+DEFAULT_WORKLOAD = "cfg2_n8192_causal"
+NOMINAL_FP16_TFLOPS = 2250.0
+
+
+def flops(B, H, N, D, causal):
+    f = 4.0 * B * H * N * N * D
+    return f / 2 if causal else f
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            m = json.load(f)
+        return {"tflops": float(m["bf16_tflops"]), "tflops_sustained": float(m.get("bf16_tflops_sustained", 0)),
+                "hbm_gbs": float(m["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {}
+        for n in dir(nv):
+            if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason"):
+                v = getattr(nv, n)
+                if isinstance(v, int) and v not in (0,):
+                    names.setdefault(v, n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bit and (bit & (bit - 1)) == 0 and mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        s = sorted(self.samples)
+        pretty = {"GpuIdle": "gpu_idle", "ApplicationsClocksSetting": "applications_clocks_setting",
+                  "SwPowerCap": "sw_power_cap", "HwSlowdown": "hw_slowdown", "SyncBoost": "sync_boost",
+                  "SwThermalSlowdown": "sw_thermal_slowdown", "HwThermalSlowdown": "hw_thermal_slowdown",
+                  "HwPowerBrakeSlowdown": "hw_power_brake_slowdown", "DisplayClockSetting": "display_clock_setting"}
+        reasons = sorted({pretty.get(r, r) for r in self.reasons} - {"gpu_idle", "None", "All"})
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(s)}
+
+
+def cpu_baseline(workload, budget_rows=None):
+    """The CPU oracle (port of cpu_attention, FA.cu:668-697) on a bounded, evenly spread row sample of
+    the same workload, all host threads.  TFLOPS-equivalent = sampled rows' FLOPs / wall time."""
+    import numpy as np
+    import _oracle
+    B, H, N, D, causal = workload
+    threads = _oracle.max_threads()
+    # ~10-20 s of CPU work: per-thread rate is ~0.5 GFLOP/s
+    target_flop = 0.5e9 * threads * 12.0
+    per_row = flops(1, 1, N, D, causal) / N
+    nrows = int(max(threads * 4, min(B * H * N, target_flop / per_row)))
+    if budget_rows:
+        nrows = budget_rows
+    rng = np.random.default_rng(0)
+    heads = min(B * H, 4)
+    shape = (1, heads, N, D)
+    q, k, v = ((rng.random(shape, dtype=np.float32) - 0.5).astype(np.float16) for _ in range(3))
+    stride = max(1, (heads * N) // nrows)
+    idx = np.arange(0, heads * N, stride)[:nrows]
+    bhs, rows = (idx // N).astype(np.int32), (idx % N).astype(np.int32)
+    if causal:
+        row_flops = float((4.0 * D * (rows.astype(np.float64) + 1)).sum())   # exact work of the sampled rows
+    else:
+        row_flops = 4.0 * D * N * len(rows)
+    t0 = time.perf_counter()
+    _oracle.attention_rows(q, k, v, causal, bhs, rows)
+    dt = time.perf_counter() - t0
+    return {"value": row_flops / dt / 1e12, "unit": "TFLOPS", "cores": threads, "kind": "port",
+            "sample": f"{len(rows)} evenly spaced rows of {heads} heads of the workload (N={N}, D={D}, "
+                      f"causal={causal}), {row_flops / 1e9:.1f} GFLOP in {dt:.1f} s; oracle/attn_oracle.c, pthreads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--sweep", action="store_true", help="also print the README-style TFLOPS table to stderr")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = world if world > 1 else args.gpus
+    workload = WORKLOADS[args.workload]
+    B, H, N, D, causal = workload
+
+    if args.impl == "reference-cpu":
+        if rank == 0:
+            cb = cpu_baseline(workload)
+            print(json.dumps({
+                "impl": "reference", "metric": "fwd_tflops", "value": cb["value"], "unit": "TFLOPS",
+                "n_gpus": 0, "steps": 1, "warmup": 0, "ms_per_step": None, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "B": B, "H": H, "N": N, "D": D, "causal": causal},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "TFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- implementations: a launcher taking device pointers + a stream, like FA.cu:606-611 ----
+    if args.impl == "ours":
+        import flash_attention_cuda_b200 as fa
+        L = fa.lib()
+
+        def launch(q, k, v, o, b, h, n, d, c, stream_ptr):
+            rc = L.flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), b, h, n, d, c, stream_ptr)
+            if rc != 0:
+                raise RuntimeError(L.flash_attn_error_string(rc).decode())
+        launches_of = fa.launch_count
+    else:
+        ref_so = os.path.join(REPO, "oracle", "_ref", "libref_v9.so")
+        if not os.path.exists(ref_so):
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable":
+                                  "oracle/_ref/libref_v9.so missing (built from /root/reference by `make -C oracle`)"}))
+            return
+        R = ctypes.CDLL(ref_so)
+        vp = ctypes.c_void_p
+        R.ref_v9_dispatch.argtypes = [vp, vp, vp, vp] + [ctypes.c_int] * 5 + [vp]
+        counter = [0]
+
+        def launch(q, k, v, o, b, h, n, d, c, stream_ptr):
+            if d != 128:
+                raise RuntimeError("the reference dispatcher hard-codes head_dim 128 (FA.cu:613)")
+            R.ref_v9_dispatch(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), b, h, n, d, c, stream_ptr)
+            counter[0] += 1
+        launches_of = lambda: counter[0]
+
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    def make_inputs(b, h, n, d, seed):
+        g = torch.Generator(device="cuda").manual_seed(seed + 1000 * rank)
+        # the reference's distribution: U(-0.5, 0.5) (FA.cu:766-768), generated on device for the big shapes
+        q, k, v = ((torch.rand((b, h, n, d), device="cuda", generator=g) - 0.5).half() for _ in range(3))
+        return q, k, v, torch.empty_like(q)
+
+    def time_kernel(b, h, n, d, c, steps, warmup):
+        q, k, v, o = make_inputs(b, h, n, d, n)
+        for _ in range(warmup):
+            launch(q, k, v, o, b, h, n, d, c, sp)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            launch(q, k, v, o, b, h, n, d, c, sp)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, (q, k, v, o)
+
+    # ---- main timed region, with clocks sampled while it runs ----
+    sampler = ClockSampler(local_rank)
+    l0 = launches_of()
+    # untimed warm-up happens inside time_kernel; sample clocks only around the whole call
+    sampler.start()
+    ms, bufs = time_kernel(B, H, N, D, causal, args.steps, args.warmup)
+    clocks = sampler.stop()
+    launches = launches_of() - l0 - args.warmup
+    fl = flops(B, H, N, D, causal)
+    tflops_rank = fl / (ms * 1e-3) / 1e12
+    value = tflops_rank * n_gpus if world > 1 else tflops_rank
+
+    # ---- e2e: host buffers through the public call, H2D + kernel + D2H timed every step ----
+    e2e_steps = args.e2e_steps or min(args.steps, 20)
+    q, k, v, o = bufs
+    nbytes = q.numel() * 2
+    hq, hk, hv = (torch.empty(q.shape, dtype=torch.float16).pin_memory() for _ in range(3))
+    ho = torch.empty(q.shape, dtype=torch.float16).pin_memory()
+    hq.copy_(q.cpu()); hk.copy_(k.cpu()); hv.copy_(v.cpu())
+    if args.impl == "ours":
+        def e2e_step():
+            rc = L.flash_attn_fwd_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), B, H, N, D, causal)
+            if rc != 0:
+                raise RuntimeError(L.flash_attn_error_string(rc).decode())
+    else:
+        def e2e_step():   # the reference harness's own sequence, FA.cu:774-780
+            q.copy_(hq, non_blocking=True); k.copy_(hk, non_blocking=True); v.copy_(hv, non_blocking=True)
+            launch(q, k, v, o, B, H, N, D, causal, sp)
+            ho.copy_(o, non_blocking=True)
+            stream.synchronize()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = fl / (e2e_ms * 1e-3) / 1e12 * (n_gpus if world > 1 else 1)
+
+    # ---- optional README-style sweep (stderr, rank 0) ----
+    sweep = None
+    if args.sweep and rank == 0:
+        sweep = {}
+        for c in (0, 1):
+            for n in (512, 768, 1024, 2048, 4096, 8192, 16384):
+                m, _ = time_kernel(1, 32, n, 128, c, 50, 5)
+                sweep[f"{'causal' if c else 'full'}_{n}"] = round(flops(1, 32, n, 128, c) / (m * 1e-3) / 1e12, 1)
+        print("sweep TFLOPS (B1 H32 D128):", json.dumps(sweep), file=sys.stderr)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    out = {
+        "metric": "fwd_tflops", "value": round(value, 2), "unit": "TFLOPS", "n_gpus": n_gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": args.workload, "B": B, "H": H, "N": N, "D": D, "causal": causal,
+                   "per_gpu": "every rank runs the full workload on its own GPU (batch x heads shard, no collective)",
+                   "l2": f"inputs {4 * nbytes / 2**20:.0f} MiB per step > 126 MB L2 (no flush needed)"
+                         if 4 * nbytes > 126e6 else "inputs fit L2: hot-L2 timing, reference method (FA.cu:942-960)",
+                   "flops_convention": "4*B*H*N^2*D, /2 causal (FA.cu:938-939)"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_val, 3), "unit": "TFLOPS", "h2d_bytes_per_step": 3 * nbytes,
+                "d2h_bytes_per_step": nbytes, "ms_per_step": round(e2e_ms, 4), "steps": e2e_steps,
+                "call": "flash_attn_fwd_host (pinned host Q,K,V -> device, kernel, O -> pinned host)"
+                        if args.impl == "ours" else "H2D x3 + flash_attention_v9_dispatch + D2H (FA.cu:774-780)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": round(tflops_rank, 2), "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": round(tflops_rank / pk["tflops"], 4), "traffic": None,
+                     "peak_source": pk["source"] + ", cuBLAS bf16 burst",
+                     "frac_of_sustained": round(tflops_rank / pk["tflops_sustained"], 4) if pk["tflops_sustained"] else None,
+                     "frac_of_nominal_2250": round(tflops_rank / NOMINAL_FP16_TFLOPS, 4),
+                     "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 4 * nbytes,
+                     "hbm_gbs_algorithmic": round(4 * nbytes / (ms * 1e-3) / 1e9, 1)},
+    }
+    if sweep:
+        out["sweep_tflops"] = sweep
+    if args.impl != "ours":
+        out["impl"] = "reference"
+        out["reference_kind"] = "V9 kernel (flash_attention_v9_dispatch) rebuilt for sm_100a, unmodified source"
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(workload)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
