@@ -103,6 +103,8 @@ def lib() -> ctypes.CDLL:
     L.flash_attn_version.restype = ctypes.c_char_p
     L.flash_attn_debug_work_item.argtypes = [ci, ci, ci, ci, ci, ci, ci, ll] + [ctypes.POINTER(ci)] * 5
     L.flash_attn_debug_work_item.restype = ci
+    L.flash_attn_debug_status.argtypes = [ctypes.POINTER(ctypes.c_uint)]
+    L.flash_attn_debug_status.restype = ci
     _lib = L
     return L
 
@@ -169,6 +171,13 @@ def kernel_info(B: int, H: int, N: int, D: int, causal: bool) -> dict:
     info = KernelInfo()
     check(lib().flash_attn_get_kernel_info(B, H, N, D, 1 if causal else 0, ctypes.byref(info)))
     return {n: getattr(info, n) for n, _ in KernelInfo._fields_}
+
+
+def watchdog_status() -> dict:
+    """Synchronises and returns the kernel watchdog record (aborted == 0 on a healthy run)."""
+    buf = (ctypes.c_uint * 4)()
+    check(lib().flash_attn_debug_status(buf))
+    return {"aborted": int(buf[0]), "tag": int(buf[1]), "block": int(buf[2]), "thread": int(buf[3])}
 
 
 def launch_count() -> int:

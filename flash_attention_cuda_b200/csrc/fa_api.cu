@@ -279,6 +279,15 @@ const char* flash_attn_version(void) { return "flashattn_b200 0.1 (sm_100a tcgen
 
 }  // extern "C"
 
+// Watchdog record of the current device: {aborted, barrier tag, block, thread} (see sm100_ptx.cuh).
+// Synchronises the device.  Returns FA_OK or a cudaError_t.
+extern "C" int flash_attn_debug_status(unsigned int* out4) {
+    if (!out4) return FA_ERR_NULL_PTR;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaMemcpyFromSymbol(out4, sm100::g_watchdog, 4 * sizeof(unsigned int));
+}
+
 // Host-side mirror of the device work decomposition, exported for the scheduler tests
 // (every (bh, q-tile) exactly once, heavy-first, masked tiles skipped).
 extern "C" int flash_attn_debug_work_item(int w, int B, int H, int Nq, int Nkv, int D, int causal, long long shift,

@@ -42,6 +42,8 @@ constexpr int kNumThreads = 384;
 constexpr int kMmaWarp = 8;
 constexpr int kLoadWarp = 9;
 constexpr int kTmemCols = 512;
+constexpr int kRegsSoftmax = 208;   // setmaxnreg: softmax warpgroups grow, the producer/MMA warpgroup shrinks
+constexpr int kRegsOther = 80;      // 2*128*208 + 128*80 = 63488 <= 168 (launch) * 384
 constexpr float kRescaleThreshold = 8.0f;  // lazy rescale: tolerate P up to 2^8 before moving the reference max
 
 template <int D>
@@ -130,14 +132,17 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
             if (i >= lim_local) s[i] = 0xff800000u;  // -inf
     }
 
-    float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-    float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+    // row max: 3-input max (FMNMX3), four independent chains
+    float mx0 = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1]));
+    float mx1 = fmaxf(__uint_as_float(s[2]), __uint_as_float(s[3]));
+    float mx2 = fmaxf(__uint_as_float(s[4]), __uint_as_float(s[5]));
+    float mx3 = fmaxf(__uint_as_float(s[6]), __uint_as_float(s[7]));
 #pragma unroll
-    for (int i = 4; i < kBlockN; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[i + 0]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+    for (int i = 8; i < kBlockN; i += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
     }
     const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
     const float m_new = fmaxf(m_ref, m_tile);
@@ -148,6 +153,7 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     if (__any_sync(0xffffffffu, need)) {
         if (have_o) {
             const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
+            const uint64_t alpha2 = pack_f32x2(alpha, alpha);
             // O_t holds PV(0..j-1); the last of them must have retired before we touch it
             mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 40);
             tc_fence_after();
@@ -157,7 +163,12 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
                 tmem_ld_x32(tO + c, o);
                 tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                for (int i = 0; i < 32; i += 2) {
+                    float lo, hi;
+                    unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), lo, hi);
+                    o[i] = __float_as_uint(lo);
+                    o[i + 1] = __float_as_uint(hi);
+                }
                 tmem_st_x32(tO + c, o);
             }
             l_run *= alpha;
@@ -167,15 +178,18 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
 
     const float m_used = (m_ref == -INFINITY) ? 0.0f : m_ref;
     const float neg = -m_used * p.scale_log2;
-    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+    const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+    const uint64_t neg2 = pack_f32x2(neg, neg);
+    uint64_t sum_a = 0ull, sum_b = 0ull;     // (0.f, 0.f)
     uint32_t pk[kBlockN / 2];
 #pragma unroll
     for (int i = 0; i < kBlockN; i += 4) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(s[i + 0]), p.scale_log2, neg));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg));
-        const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), p.scale_log2, neg));
-        const float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), p.scale_log2, neg));
-        sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;   // row sum of the un-rounded p (FA.cu:273-279)
+        float x0, x1, x2, x3;
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[i + 0]), __uint_as_float(s[i + 1])), scale2, neg2), x0, x1);
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])), scale2, neg2), x2, x3);
+        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+        sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));      // row sum of the un-rounded p (FA.cu:273-279)
+        sum_b = add_f32x2(sum_b, pack_f32x2(p2, p3));
         __half2 h01 = __floats2half2_rn(p0, p1);           // low half = even column
         __half2 h23 = __floats2half2_rn(p2, p3);
         pk[i / 2 + 0] = *reinterpret_cast<uint32_t*>(&h01);
@@ -186,8 +200,12 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     tmem_st_x32(tS + 32, pk + 32);
     tmem_wait_st();
     tc_fence_before();
-    mbar_arrive(bar_p_full);
-    l_run += (sum0 + sum1) + (sum2 + sum3);
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(bar_p_full);           // one arrival per warp (barrier count 4)
+    float a0, a1, b0, b1;
+    unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
+    (void)b0; (void)b1;
+    l_run += a0 + a1;
 }
 
 template <int D>
@@ -223,7 +241,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
         for (int t = 0; t < 2; t++) {
             mbar_init(bar_s_full + 8 * t, 1);
-            mbar_init(bar_p_full + 8 * t, kBlockM);   // every softmax thread of the tile arrives
+            mbar_init(bar_p_full + 8 * t, 4);         // one arrival per softmax warp of the tile
             mbar_init(bar_o_full + 8 * t, 1);
         }
         fence_mbar_init();
@@ -242,116 +260,144 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
+    // The producer and MMA warps run their loops converged (all 32 lanes take the same branches
+    // and waits); the instructions with side effects sit under elect_one().  Warp-uniform control
+    // flow keeps descriptors and barrier addresses in uniform registers -- in a lane-divergent
+    // region every UTCHMMA costs an extra ELECT / R2UR.BROADCAST sequence and the single issuing
+    // thread becomes the bottleneck of the whole CTA (profiles/r01_v1_full_n8192_summary.txt).
+    if (warp >= 8) {
+    setmaxnreg_dec<kRegsOther>();   // each role's code must be dominated by its own setmaxnreg
     if (warp == kLoadWarp) {
         // =============================== TMA producer ===============================
-        if (lane == 0) {
-            Ring ring{0u, 0u};
-            uint32_t it = 0;
-            for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
-                const WorkItem wi = decode_work(w, p);
-                const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
-                const bool have_q1 = wi.q0 + kBlockM < p.Nq;
-                mbar_wait(bar_q_empty, (it & 1u) ^ 1u, 1);   // previous item's QK^T MMAs retired
+        Ring ring{0u, 0u};
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+            const WorkItem wi = decode_work(w, p);
+            const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
+            const bool have_q1 = wi.q0 + kBlockM < p.Nq;
+            mbar_wait(bar_q_empty, (it & 1u) ^ 1u, 1);   // previous item's QK^T MMAs retired
+            if (elect_one()) {
                 mbar_arrive_expect_tx(bar_q_full, (have_q1 ? 2 : 1) * C::kTileBytes);
                 for (int t = 0; t < (have_q1 ? 2 : 1); t++)
                     for (int pn = 0; pn < C::kPanels; pn++)
                         tma_load_3d(sQ + t * C::kTileBytes + pn * C::kPanelBytes, &tmQ, bar_q_full, pn * 64,
                                     wi.q0 + t * kBlockM, wi.bh);
-                for (int j = 0; j < nmax; j++) {
-                    // ring order K_0 V_0 K_1 V_1 ... (the order the MMA warp releases them in)
-                    for (int kv = 0; kv < 2; kv++) {
-                        const uint32_t full = bar_kv_full + 8 * ring.idx;
-                        mbar_wait(bar_kv_empty + 8 * ring.idx, ring.phase ^ 1u, 2);
+            }
+            __syncwarp();
+            for (int j = 0; j < nmax; j++) {
+                // ring order K_0 V_0 K_1 V_1 ... (the order the MMA warp releases them in)
+#pragma unroll
+                for (int kv = 0; kv < 2; kv++) {
+                    const uint32_t full = bar_kv_full + 8 * ring.idx;
+                    mbar_wait(bar_kv_empty + 8 * ring.idx, ring.phase ^ 1u, 2);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(full, C::kTileBytes);
                         const uint32_t dst = sKV + ring.idx * C::kTileBytes;
+#pragma unroll
                         for (int pn = 0; pn < C::kPanels; pn++)
                             tma_load_3d(dst + pn * C::kPanelBytes, kv == 0 ? &tmK : &tmV, full, pn * 64,
                                         j * kBlockN, wi.bh);
-                        ring.advance<C::kStages>();
                     }
+                    __syncwarp();
+                    ring.advance<C::kStages>();
                 }
             }
         }
     } else if (warp == kMmaWarp) {
         // =============================== tcgen05.mma issuer ===============================
-        if (lane == 0) {
-            Ring rk{0u, 0u};              // ring entry holding K_j
-            Ring rv{1u % C::kStages, 0u}; // ring entry holding V_j
-            uint32_t it = 0;
-            uint32_t p_phase[2] = {0u, 0u};
-            const uint32_t tS[2] = {tmem_base + C::kTmemS0, tmem_base + C::kTmemS1};
-            const uint32_t tO[2] = {tmem_base + C::kTmemO0, tmem_base + C::kTmemO1};
+        Ring rk{0u, 0u};              // ring entry holding K_j
+        Ring rv{1u % C::kStages, 0u}; // ring entry holding V_j
+        uint32_t it = 0;
+        uint32_t p_phase0 = 0u, p_phase1 = 0u;
+        const uint32_t tS0 = tmem_base + C::kTmemS0, tS1 = tmem_base + C::kTmemS1;
+        const uint32_t tO0 = tmem_base + C::kTmemO0, tO1 = tmem_base + C::kTmemO1;
+        const uint64_t qdesc0 = umma_smem_desc(sQ, 16, 1024);
+        const uint64_t qdesc1 = umma_smem_desc(sQ + C::kTileBytes, 16, 1024);
 
-            // S_t = Q_t K_j^T : D/16 k-steps; k-step ks lives in panel ks/4 at byte offset (ks%4)*32
-            auto issue_qk = [&](int t, uint32_t k_smem) {
+        // S_t = Q_t K_j^T : D/16 k-steps; k-step ks lives in panel ks/4 at byte offset (ks%4)*32
+        auto issue_qk = [&](uint32_t tS, uint64_t qdesc, uint32_t k_smem, uint32_t bar) {
+            const uint64_t kdesc = umma_smem_desc(k_smem, 16, 1024);
+            if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < D / 16; ks++) {
-                    const uint32_t off = (ks >> 2) * C::kPanelBytes + (ks & 3) * 32;
-                    const uint64_t ad = umma_smem_desc(sQ + t * C::kTileBytes + off, 16, 1024);
-                    const uint64_t bd = umma_smem_desc(k_smem + off, 16, 1024);
-                    umma_ss(tS[t], ad, bd, C::kIdescQK, ks > 0 ? 1u : 0u);
+                    const uint64_t off = (uint64_t)(((ks >> 2) * C::kPanelBytes + (ks & 3) * 32) >> 4);
+                    umma_ss(tS, qdesc + off, kdesc + off, C::kIdescQK, ks > 0 ? 1u : 0u);
                 }
-                umma_commit(bar_s_full + 8 * t);
-            };
-            // O_t (+)= P_t V_j : 8 k-steps of 16 kv rows; P k-step = 8 TMEM columns, V k-step = 16 rows * 128 B
-            auto issue_pv = [&](int t, uint32_t v_smem, bool accumulate) {
+                umma_commit(bar);
+            }
+            __syncwarp();
+        };
+        // O_t (+)= P_t V_j : 8 k-steps of 16 kv rows; P k-step = 8 TMEM columns, V k-step = 16 rows * 128 B
+        auto issue_pv = [&](uint32_t tO, uint32_t tP, uint32_t v_smem, bool accumulate, uint32_t bar) {
+            const uint64_t vdesc = umma_smem_desc(v_smem, C::kPanelBytes, 1024);
+            if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < kBlockN / 16; ks++) {
-                    const uint64_t bd = umma_smem_desc(v_smem + ks * 16 * 128, C::kPanelBytes, 1024);
-                    umma_ts(tO[t], tS[t] + ks * 8, bd, C::kIdescPV, (accumulate || ks > 0) ? 1u : 0u);
-                }
-                umma_commit(bar_o_full + 8 * t);
-            };
+                for (int ks = 0; ks < kBlockN / 16; ks++)
+                    umma_ts(tO, tP + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV,
+                            (accumulate || ks > 0) ? 1u : 0u);
+                umma_commit(bar);
+            }
+            __syncwarp();
+        };
+        auto commit = [&](uint32_t bar) {
+            if (elect_one()) umma_commit(bar);
+            __syncwarp();
+        };
 
-            for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
-                const WorkItem wi = decode_work(w, p);
-                const int n[2] = {wi.n0, wi.n1};
-                const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
-                mbar_wait(bar_q_full, it & 1u, 10);
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+            const WorkItem wi = decode_work(w, p);
+            const int n0 = wi.n0, n1 = wi.n1;
+            const int nmax = n0 > n1 ? n0 : n1;
+            mbar_wait(bar_q_full, it & 1u, 10);
+            tc_fence_after();
+            if (nmax > 0) {
+                mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 11);
                 tc_fence_after();
-                if (nmax > 0) {
-                    mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 11);
+                const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
+                if (n0 > 0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
+                if (n1 > 0) issue_qk(tS1, qdesc1, k_smem, bar_s_full + 8);
+                commit(bar_kv_empty + 8 * rk.idx);
+                rk.advance<C::kStages>(); rk.advance<C::kStages>();
+            }
+            // Q is free for the next item as soon as the last QK^T of this one has retired
+            if (nmax <= 1) commit(bar_q_empty);
+            for (int j = 0; j < nmax; j++) {
+                const bool has_next = j + 1 < nmax;
+                mbar_wait(bar_kv_full + 8 * rv.idx, rv.phase, 12);
+                const uint32_t v_smem = sKV + rv.idx * C::kTileBytes;
+                const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
+                // ---- tile 0: PV0(j), QK0(j+1)
+                if (j < n0) {
+                    mbar_wait(bar_p_full, p_phase0, 13);
+                    p_phase0 ^= 1u;
                     tc_fence_after();
-                    const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
-                    if (n[0] > 0) issue_qk(0, k_smem);
-                    if (n[1] > 0) issue_qk(1, k_smem);
-                    umma_commit(bar_kv_empty + 8 * rk.idx);
-                    rk.advance<C::kStages>(); rk.advance<C::kStages>();
+                    issue_pv(tO0, tS0, v_smem, j > 0, bar_o_full);
                 }
-                // Q is free for the next item as soon as the last QK^T of this one has retired
-                if (nmax <= 1) umma_commit(bar_q_empty);
-                for (int j = 0; j < nmax; j++) {
-                    const bool has_next = j + 1 < nmax;
-                    mbar_wait(bar_kv_full + 8 * rv.idx, rv.phase, 12);
-                    const uint32_t v_smem = sKV + rv.idx * C::kTileBytes;
-                    const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
-#pragma unroll
-                    for (int t = 0; t < 2; t++) {
-                        if (j < n[t]) {
-                            mbar_wait(bar_p_full + 8 * t, p_phase[t], 13 + t);
-                            p_phase[t] ^= 1u;
-                            tc_fence_after();
-                            issue_pv(t, v_smem, j > 0);
-                        }
-                        if (t == 0 && has_next) {
-                            mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 15);
-                            tc_fence_after();
-                        }
-                        if (t == 1) {
-                            umma_commit(bar_kv_empty + 8 * rv.idx);
-                            rv.advance<C::kStages>(); rv.advance<C::kStages>();
-                        }
-                        if (j + 1 < n[t]) issue_qk(t, k_smem);
-                    }
-                    if (has_next) {
-                        umma_commit(bar_kv_empty + 8 * rk.idx);
-                        rk.advance<C::kStages>(); rk.advance<C::kStages>();
-                        if (j + 2 == nmax) umma_commit(bar_q_empty);   // QK^T(nmax-1) was the last reader of Q
-                    }
+                if (has_next) {
+                    mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 15);
+                    tc_fence_after();
+                }
+                if (j + 1 < n0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
+                // ---- tile 1: PV1(j), QK1(j+1)
+                if (j < n1) {
+                    mbar_wait(bar_p_full + 8, p_phase1, 14);
+                    p_phase1 ^= 1u;
+                    tc_fence_after();
+                    issue_pv(tO1, tS1, v_smem, j > 0, bar_o_full + 8);
+                }
+                commit(bar_kv_empty + 8 * rv.idx);
+                rv.advance<C::kStages>(); rv.advance<C::kStages>();
+                if (j + 1 < n1) issue_qk(tS1, qdesc1, k_smem, bar_s_full + 8);
+                if (has_next) {
+                    commit(bar_kv_empty + 8 * rk.idx);
+                    rk.advance<C::kStages>(); rk.advance<C::kStages>();
+                    if (j + 2 == nmax) commit(bar_q_empty);   // QK^T(nmax-1) was the last reader of Q
                 }
             }
         }
-    } else if (warp < 8) {
+    }
+    } else {
+        setmaxnreg_inc<kRegsSoftmax>();
         // =============================== softmax / correction / epilogue ===============================
         const int t = warp >> 2;                               // which Q tile of the pair
         const int row_in_tile = (warp & 3) * 32 + lane;        // TMEM lane == S/O row

@@ -19,6 +19,26 @@ __device__ __forceinline__ uint32_t lane_id() {
     return l;
 }
 
+// One lane of a converged warp (elect.sync).  Code under `if (elect_one())` keeps warp-uniform
+// operands in uniform registers, which is what UTCHMMA / UTMALDG / UTCBAR consume.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -44,20 +64,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Blocking wait with a watchdog: a protocol bug shows up as a trapped kernel with the
-// barrier's tag printed, not as a hung GPU.  ~2^32 cycles is >1.5 s; no legitimate wait in
-// these kernels is longer than a few milliseconds.
-__device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
-    printf("[fa_sm100] mbarrier wait timed out: block %d thread %d tag %d parity %u\n",
-           (int)blockIdx.x, (int)threadIdx.x, tag, parity);
-    __trap();
+// Blocking wait with a watchdog.  A protocol bug must not hang the GPU: after ~2^31 cycles (>1 s;
+// no legitimate wait here exceeds a few ms) the waiter records who it was in g_watchdog and raises
+// a device-wide abort flag; every wait that is in its slow path then returns at once, so the
+// kernel drains and exits with garbage results instead of spinning.  The host reads the record
+// through flash_attn_debug_status().  No function call / printf here on purpose: a call in the
+// kernel makes ptxas ignore the per-role setmaxnreg budgets and spill the softmax warps.
+__device__ unsigned int g_watchdog[4];   // {abort flag, barrier tag, block, thread}
+__device__ __forceinline__ bool watchdog_aborted() {
+    return *reinterpret_cast<volatile unsigned int*>(&g_watchdog[0]) != 0u;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 63u) == 0u && clock64() - t0 > (1ll << 32)) mbar_timeout(tag, parity);
+        if ((++polls & 63u) == 0u) {
+            if (watchdog_aborted()) return;
+            if (clock64() - t0 > (1ll << 31)) {
+                if (atomicExch(&g_watchdog[0], 1u) == 0u) {
+                    g_watchdog[1] = (unsigned)tag;
+                    g_watchdog[2] = blockIdx.x;
+                    g_watchdog[3] = threadIdx.x;
+                }
+                return;
+            }
+        }
     }
 }
 
@@ -234,6 +266,35 @@ __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {   // FMNMX3
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2): two lanes per instruction on the FMA pipe
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
 }
 
 }  // namespace sm100

@@ -22,6 +22,9 @@ def run_gpu(q, k, v, causal):
     tq, tk, tv = (torch.from_numpy(x).cuda() for x in (q, k, v))
     out = fa.flash_attn_fwd(tq, tk, tv, causal=causal)
     torch.cuda.synchronize()
+    wd = fa.watchdog_status()
+    if wd["aborted"]:
+        print("   !! kernel watchdog fired:", wd, flush=True)
     return out.cpu().numpy()
 
 

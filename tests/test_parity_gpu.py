@@ -29,6 +29,8 @@ def gpu_attention(fa, q, k, v, causal):
     out = fa.flash_attn_fwd(tq, tk, tv, causal=bool(causal))
     torch.cuda.synchronize()
     assert fa.launch_count() == before + 1, "the CUDA kernel was not launched"
+    wd = fa.watchdog_status()
+    assert not wd["aborted"], f"kernel watchdog fired (mbarrier wait timed out): {wd}"
     return out.cpu().numpy()
 
 
