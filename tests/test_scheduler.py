@@ -31,7 +31,8 @@ def test_every_q_tile_exactly_once(N, causal):
                 assert (it["bh"], q_start) not in seen
                 seen.add((it["bh"], q_start))
                 last_row = min(q_start + 127, N - 1)
-                want = (min(N, last_row + 1) + 127) // 128 if causal else (N + 127) // 128
+                # trip counts are in 64-wide KV sub-tiles (fa::kSubN)
+                want = (min(N, last_row + 1) + 63) // 64 if causal else (N + 63) // 64
                 assert n == want, (it, t)
             else:
                 assert n == 0
@@ -53,12 +54,12 @@ def test_masked_tiles_skipped_with_offsets():
     assert all(it["n0"] == 0 and it["n1"] == 0 for it in its)
     # block entirely in the past: every tile needs all KV tiles, as in non-causal
     its = items(1, 1, 512, 512, 128, True, shift=512)
-    assert all(it["n0"] == 4 and it["n1"] == 4 for it in its)
+    assert all(it["n0"] == 8 and it["n1"] == 8 for it in its)
 
 
 def test_total_causal_tiles_is_triangular():
     N = 8192
     its = items(1, 1, N, N, 128, True)
     tiles = sum(it["n0"] + it["n1"] for it in its)
-    n = N // 128
-    assert tiles == n * (n + 1) // 2
+    n = N // 128          # q tiles; q tile i needs 2*(i+1) sub-tiles of 64 keys
+    assert tiles == n * (n + 1)
