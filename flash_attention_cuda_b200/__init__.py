@@ -17,7 +17,8 @@ import subprocess
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_PKG_DIR)
-LIB_PATH = os.path.join(_PKG_DIR, "libflashattn_b200.so")
+# FLASH_ATTN_B200_LIB selects another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("FLASH_ATTN_B200_LIB") or os.path.join(_PKG_DIR, "libflashattn_b200.so")
 
 FA_OK = 0
 ERRORS = {

@@ -16,6 +16,7 @@
 namespace {
 
 constexpr int kMaxDevices = 64;
+constexpr int kSchedSlots = 4096;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -31,6 +32,10 @@ struct DeviceState {
     int ok = 0;           // cudaSuccess when attributes are set
     int num_sms = 0;
     int cc_major = 0;
+    // dynamic tile scheduler state: kSchedSlots x {next, done} ints, zero when idle; a launch uses
+    // slot (sequence number % kSchedSlots) and its last CTA re-zeroes it
+    int* sched = nullptr;
+    std::atomic<unsigned> sched_seq{0};
     // staging buffers for flash_attn_fwd_host
     std::mutex host_mu;
     void* stage = nullptr;
@@ -70,6 +75,8 @@ DeviceState* device_state(int* err) {
         if (prop.major != 10) { st->ok = FA_ERR_UNSUPPORTED_ARCH; return; }
         int r = set_kernel_attrs<128>();
         if (r == 0) r = set_kernel_attrs<64>();
+        if (r == 0) r = (int)cudaMalloc(&st->sched, kSchedSlots * 2 * sizeof(int));
+        if (r == 0) r = (int)cudaMemset(st->sched, 0, kSchedSlots * 2 * sizeof(int));
         st->ok = r;
     });
     if (st->ok != 0) { *err = st->ok; return nullptr; }
@@ -110,16 +117,23 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     p.nqp = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
     const long long tw = (long long)BH * p.nqp;
     p.total_work = (int)tw;
+    // heads per scheduling group: K+V of the group <= 64 MB (half of B200's 126 MB L2)
+    const long long kv_bytes = 2LL * Nkv * D * 2;
+    long long gh = (64LL << 20) / (kv_bytes > 0 ? kv_bytes : 1);
+    if (gh < 1) gh = 1;
+    if (gh > BH) gh = BH;
+    p.group_heads = (int)gh;
     p.scale = 1.0f / sqrtf((float)D);             // FA.cu:612
     p.scale_log2 = p.scale * 1.4426950408889634f;
     return p;
 }
 
 template <int D>
-int launch(const DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-           const fa::Params& p, cudaStream_t stream) {
+int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+           fa::Params p, cudaStream_t stream) {
     int grid = p.total_work < st->num_sms ? p.total_work : st->num_sms;
     if (grid < 1) grid = 1;
+    p.sched = st->sched + 2 * (st->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
     fa::fa_fwd_kernel<D><<<grid, fa::kNumThreads, fa::Cfg<D>::kSmemBytes, stream>>>(tq, tk, tv, p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();   // FA.cu:662

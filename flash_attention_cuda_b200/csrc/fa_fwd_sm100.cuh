@@ -19,12 +19,15 @@
 // One CTA per SM; each CTA loops over work items (bh, pair of 128-row Q tiles).
 //
 // TMEM (512 columns x 128 lanes x 32 bit): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).
-// The KV axis is processed in 64-column sub-tiles u = 0,1,2,...: sub-tile u of Q tile t lives in half
-// (u & 1) of S_t, so S is double-buffered per Q tile: QK_t(u+2) is issued right behind PV_t(u) and a
-// softmax warpgroup never waits for "its own" MMAs -- while it turns S_t(u) into P_t(u), S_t(u+1) is
-// already in TMEM.  P_t(u) (fp16, two per column) overwrites columns [0,32) of its S half once the
-// owning thread has read its S row.  Tensor-pipe order: PV0(u) QK0(u+2) PV1(u) QK1(u+2).
-// K/V stay 128-row smem tiles (one TMA ring entry each); a sub-tile is half of one.
+// P_t (fp16, two per column) overwrites columns [0,64) of S_t once the owning thread has read
+// its S row, and is handed to the MMA warp in two halves (keys 0-63, 64-127) so that the first four
+// PV k-steps run while the second half of the exponentials is still being computed.
+// Tensor-pipe order per KV tile j:  PV0(j) QK0(j+1) PV1(j) QK1(j+1), so each softmax warpgroup works
+// on S_t(j+1) while the tensor core runs the other tile's two MMAs.
+//
+// Why not 64-wide KV sub-tiles with S double-buffered (tried, profiles/r01_v3_subtile_*): QK^T with
+// N=64 in SS mode re-reads the Q slice from shared memory for half the math (192 B/clk > the 128 B/clk
+// smem port).  N=128 sits exactly at the port limit, so the S->P->PV->QK chain is shortened instead.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -40,15 +43,21 @@ namespace fa {
 using namespace sm100;
 
 constexpr int kBlockM = 128;      // Q rows per tile  (UMMA M)
-constexpr int kBlockN = 128;      // K/V rows per smem tile (one TMA ring entry)
-constexpr int kSubN = 64;         // K/V rows per MMA/softmax sub-tile (UMMA N of QK^T, K extent of PV)
+constexpr int kBlockN = 128;      // K/V rows per tile (UMMA N of QK^T, K extent of PV)
 constexpr int kNumThreads = 384;
 constexpr int kMmaWarp = 8;
 constexpr int kLoadWarp = 9;
 constexpr int kTmemCols = 512;
 constexpr int kRegsSoftmax = 208;   // setmaxnreg: softmax warpgroups grow, the producer/MMA warpgroup shrinks
 constexpr int kRegsOther = 80;      // 2*128*208 + 128*80 = 63488 <= 168 (launch) * 384
-constexpr float kRescaleThreshold = 8.0f;  // lazy rescale: tolerate P up to 2^8 before moving the reference max
+constexpr float kRescaleThreshold = 8.0f;
+// Of every 4 element pairs, this many take exp2 on the FMA pipe (Cody-Waite + degree-3 minimax)
+// instead of MUFU.EX2: at 16 MUFU/clk/SM the 16384 exponentials of a 128x128 tile cost as many
+// cycles as its two MMAs, so the SFU -- not the tensor core -- would set the pace.
+#ifndef FA_POLY_PAIRS
+#define FA_POLY_PAIRS 1
+#endif
+constexpr int kPolyPairs = FA_POLY_PAIRS;  // lazy rescale: tolerate P up to 2^8 before moving the reference max
 
 template <int D>
 struct Cfg {
@@ -60,10 +69,10 @@ struct Cfg {
     static constexpr int kSmemQ = 2 * kTileBytes;
     static constexpr int kSmemKV = kStages * kTileBytes;
     static constexpr int kBarOffset = kSmemQ + kSmemKV;
-    static constexpr int kNumBars = 2 + 2 * kStages + 12;
-    static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 16 + 1024;  // +1024: manual alignment slack
+    static constexpr int kNumBars = 2 + 2 * kStages + 8 + 4;
+    static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 32 + 1024;  // +32: tmem slot, scheduler slots; +1024: manual alignment slack
     static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
-    static constexpr uint32_t kIdescQK = umma_idesc_f16(kBlockM, kSubN, 0, 0);
+    static constexpr uint32_t kIdescQK = umma_idesc_f16(kBlockM, kBlockN, 0, 0);
     static constexpr uint32_t kIdescPV = umma_idesc_f16(kBlockM, D, 0, 1);  // V is MN-major ([kv][d], d contiguous)
 };
 
@@ -76,8 +85,10 @@ struct Params {
     int shift;          // q_offset - kv_offset: key c visible to query r iff c <= r + shift
     int nqp;            // Q tile pairs per head = ceil(Nq / 256)
     int total_work;     // BH * nqp
+    int group_heads;    // heads per scheduling group (their K/V working set is sized to stay in L2)
     int partial_mode;
     int accumulate;
+    int* sched;         // {next work index, finished CTAs}: dynamic tile scheduler state, self-resetting
     float scale;        // 1/sqrt(D)
     float scale_log2;   // scale * log2(e)
 };
@@ -85,26 +96,33 @@ struct Params {
 // ---- work decomposition (shared by host tests and every warp role) ----
 struct WorkItem {
     int bh, q0;      // head index, first local query row of the pair
-    int n0, n1;      // 64-wide KV sub-tiles the two Q tiles need (0 = nothing visible / tile absent)
+    int n0, n1;      // KV tiles the two Q tiles need (0 = nothing visible / tile absent)
 };
 __host__ __device__ inline int kv_trip_count(int q_start, int Nq, int Nkv, int causal, int shift) {
     if (q_start >= Nq) return 0;
-    long long vis = Nkv;                              // keys [0, vis) are visible to the tile's last row
-    if (causal) {
-        int last_row = q_start + kBlockM - 1;
-        if (last_row > Nq - 1) last_row = Nq - 1;
-        vis = (long long)last_row + shift + 1;
-        if (vis <= 0) return 0;
-        if (vis > Nkv) vis = Nkv;
-    }
-    return (int)((vis + kSubN - 1) / kSubN);
+    const int nkv_tiles = (Nkv + kBlockN - 1) / kBlockN;
+    if (!causal) return nkv_tiles;
+    int last_row = q_start + kBlockM - 1;
+    if (last_row > Nq - 1) last_row = Nq - 1;
+    long long vis = (long long)last_row + shift + 1;  // keys [0, vis) visible to the last row
+    if (vis <= 0) return 0;
+    if (vis > Nkv) vis = Nkv;
+    return (int)((vis + kBlockN - 1) / kBlockN);
 }
-// Work order: heads outermost (the CTAs running concurrently share a few heads' K/V in L2),
-// heaviest Q pair first inside a head (causal: the last pair sees the most keys).
+// Work order (replaces GRID_SWAP / reversed q-blocks, FA.cu:103-112).  Heads are taken in groups whose
+// K/V fit comfortably in L2; inside a group the order is heaviest Q pair first ACROSS the group's
+// heads (causal: the last pair sees the most keys), so the dynamic scheduler hands out long items
+// early and the tail of the launch is made of the lightest ones, while the CTAs running at any moment
+// still share a few heads' K/V through L2.
 __host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
     WorkItem it;
-    it.bh = w / p.nqp;
-    const int qp = p.nqp - 1 - (w % p.nqp);
+    const int per_group = p.group_heads * p.nqp;
+    const int g = w / per_group;
+    const int r = w - g * per_group;
+    int heads = p.BH - g * p.group_heads;
+    if (heads > p.group_heads) heads = p.group_heads;
+    const int qp = p.nqp - 1 - r / heads;
+    it.bh = g * p.group_heads + r % heads;
     it.q0 = qp * 2 * kBlockM;
     it.n0 = kv_trip_count(it.q0, p.Nq, p.Nkv, p.causal, p.shift);
     it.n1 = kv_trip_count(it.q0 + kBlockM, p.Nq, p.Nkv, p.causal, p.shift);
@@ -119,19 +137,75 @@ struct Ring {
     }
 };
 
-// ---- softmax of one 128x64 S sub-tile; one thread owns one row ----
+// ---- exp2 of a pair of (already scaled and shifted) scores ----
+// kPoly = false: two MUFU.EX2.  kPoly = true: FMA/ALU pipes only.  x = n + f, n = round(x),
+// f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, below the
+// 4.9e-4 of the fp16 rounding P gets anyway); 2^n by adding n into the exponent field.
+template <bool kPoly>
+__device__ __forceinline__ void exp2_pair(uint64_t x2, float& p0, float& p1) {
+    if (!kPoly) {
+        float x0, x1;
+        unpack_f32x2(x2, x0, x1);
+        p0 = ex2_approx(x0);
+        p1 = ex2_approx(x1);
+    } else {
+        float x0, x1;
+        unpack_f32x2(x2, x0, x1);
+        x0 = fmaxf(x0, -126.0f);                       // masked (-inf) and far-away scores -> 2^-126 ~ 0
+        x1 = fmaxf(x1, -126.0f);
+        x2 = pack_f32x2(x0, x1);
+        const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);        // 1.5 * 2^23: rounds to integer
+        const uint64_t t2 = add_f32x2(x2, magic);
+        const uint64_t n2 = add_f32x2(t2, pack_f32x2(-12582912.0f, -12582912.0f));
+        const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.0f, -1.0f), x2);
+        uint64_t q2 = fma_f32x2(pack_f32x2(0.05517143756151199f, 0.05517143756151199f), f2,
+                                pack_f32x2(0.24261081218719482f, 0.24261081218719482f));
+        q2 = fma_f32x2(q2, f2, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+        q2 = fma_f32x2(q2, f2, pack_f32x2(0.9999281167984009f, 0.9999281167984009f));
+        float t0, t1, q0, q1;
+        unpack_f32x2(t2, t0, t1);
+        unpack_f32x2(q2, q0, q1);
+        p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+        p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+    }
+}
+
+// exponentials + fp16 packing of 64 consecutive columns (one half of the tile)
+__device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64_t scale2, uint64_t neg2,
+                                         uint64_t& sum_a, uint64_t& sum_b) {
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int e = i + 2 * q;
+            const uint64_t x2 =
+                fma_f32x2(pack_f32x2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, neg2);
+            float p0, p1;
+            if (q < kPolyPairs) exp2_pair<true>(x2, p0, p1);
+            else exp2_pair<false>(x2, p0, p1);
+            if (q & 1) sum_b = add_f32x2(sum_b, pack_f32x2(p0, p1));   // row sum of the un-rounded p (FA.cu:273-279)
+            else sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
+            __half2 h = __floats2half2_rn(p0, p1);                     // low half = even column
+            pk[e / 2] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+}
+
+// ---- softmax of one 128x128 S tile; one thread owns one row ----
 template <int D, bool kMask>
-__device__ __forceinline__ void softmax_subtile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
-                                                uint32_t bar_o_full, int lim_local, bool have_o,
-                                                uint32_t pv_count, float& m_ref, float& l_run) {
-    uint32_t s[kSubN];
+__device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
+                                             uint32_t bar_o_full, int lim_local, bool have_o,
+                                             uint32_t pv_count, float& m_ref, float& l_run) {
+    uint32_t s[kBlockN];
     tmem_ld_x32(tS + 0, s + 0);
     tmem_ld_x32(tS + 32, s + 32);
+    tmem_ld_x32(tS + 64, s + 64);
+    tmem_ld_x32(tS + 96, s + 96);
     tmem_wait_ld();
 
     if (kMask) {
 #pragma unroll
-        for (int i = 0; i < kSubN; i++)
+        for (int i = 0; i < kBlockN; i++)
             if (i >= lim_local) s[i] = 0xff800000u;  // -inf
     }
 
@@ -141,7 +215,7 @@ __device__ __forceinline__ void softmax_subtile(const Params& p, uint32_t tS, ui
     float mx2 = fmaxf(__uint_as_float(s[4]), __uint_as_float(s[5]));
     float mx3 = fmaxf(__uint_as_float(s[6]), __uint_as_float(s[7]));
 #pragma unroll
-    for (int i = 8; i < kSubN; i += 8) {
+    for (int i = 8; i < kBlockN; i += 8) {
         mx0 = fmax3(mx0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
         mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
         mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
@@ -157,9 +231,7 @@ __device__ __forceinline__ void softmax_subtile(const Params& p, uint32_t tS, ui
         if (have_o) {
             const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
             const uint64_t alpha2 = pack_f32x2(alpha, alpha);
-            // O_t holds PV(0..u-1); the last of them must have retired before we touch it.  PV(u-2)
-            // and older are known to be complete (S(u) is ready and the tensor pipe is in order), so
-            // the barrier of PV(u-1)'s parity is at most one phase behind: the parity test is exact.
+            // O_t holds PV(0..j-1); the last of them must have retired before we touch it
             mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 40);
             tc_fence_after();
 #pragma unroll
@@ -186,26 +258,18 @@ __device__ __forceinline__ void softmax_subtile(const Params& p, uint32_t tS, ui
     const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
     const uint64_t neg2 = pack_f32x2(neg, neg);
     uint64_t sum_a = 0ull, sum_b = 0ull;     // (0.f, 0.f)
-    uint32_t pk[kSubN / 2];
+    uint32_t pk[32];
+    // P_t (fp16 A operand of PV) overwrites columns [0,64) of S_t, delivered in two halves:
+    // keys 0-63 -> columns [0,32) -> barrier half 0, keys 64-127 -> columns [32,64) -> half 1
 #pragma unroll
-    for (int i = 0; i < kSubN; i += 4) {
-        float x0, x1, x2, x3;
-        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[i + 0]), __uint_as_float(s[i + 1])), scale2, neg2), x0, x1);
-        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])), scale2, neg2), x2, x3);
-        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
-        sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));      // row sum of the un-rounded p (FA.cu:273-279)
-        sum_b = add_f32x2(sum_b, pack_f32x2(p2, p3));
-        __half2 h01 = __floats2half2_rn(p0, p1);           // low half = even column
-        __half2 h23 = __floats2half2_rn(p2, p3);
-        pk[i / 2 + 0] = *reinterpret_cast<uint32_t*>(&h01);
-        pk[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&h23);
+    for (int h = 0; h < 2; h++) {
+        exp_half(s + 64 * h, pk, scale2, neg2, sum_a, sum_b);
+        tmem_st_x32(tS + 32 * h, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(bar_p_full + 8 * h);   // one arrival per warp (barrier count 4)
     }
-    // P (fp16 A operand of PV) overwrites columns [0,32) of this S half
-    tmem_st_x32(tS, pk);
-    tmem_wait_st();
-    tc_fence_before();
-    __syncwarp();
-    if (lane_id() == 0) mbar_arrive(bar_p_full);           // one arrival per warp (barrier count 4)
     float a0, a1;
     unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
     l_run += a0 + a1;
@@ -226,11 +290,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t bar_q_empty = bars + 8;
     const uint32_t bar_kv_full = bars + 16;                       // [kStages]
     const uint32_t bar_kv_empty = bar_kv_full + 8 * C::kStages;   // [kStages]
-    const uint32_t bar_s_full = bar_kv_empty + 8 * C::kStages;    // [tile][half]  index 2*t + h
-    const uint32_t bar_p_full = bar_s_full + 32;                  // [tile][half]
-    const uint32_t bar_o_full = bar_p_full + 32;                  // [tile][half]: PV_t(u) commits to half u & 1
-    const uint32_t tmem_slot = bar_o_full + 32;
+    const uint32_t bar_s_full = bar_kv_empty + 8 * C::kStages;    // [tile]
+    const uint32_t bar_p_full = bar_s_full + 16;                  // [tile][half]  index 2*t + h
+    const uint32_t bar_o_full = bar_p_full + 32;                  // [tile]
+    const uint32_t bar_sched_full = bar_o_full + 16;              // [2] work-index slots, producer -> everyone
+    const uint32_t bar_sched_empty = bar_sched_full + 16;         // [2]
+    const uint32_t tmem_slot = bar_sched_empty + 16;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    volatile int* sched_w = reinterpret_cast<volatile int*>(tmem_slot_ptr + 2);   // [2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -242,11 +309,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             mbar_init(bar_kv_full + 8 * i, 1);
             mbar_init(bar_kv_empty + 8 * i, 1);
         }
-        for (int i = 0; i < 4; i++) {
-            mbar_init(bar_s_full + 8 * i, 1);
-            mbar_init(bar_p_full + 8 * i, 4);         // one arrival per softmax warp of the tile
+        for (int t = 0; t < 2; t++) {
+            mbar_init(bar_s_full + 8 * t, 1);
+            mbar_init(bar_p_full + 16 * t, 4);        // one arrival per softmax warp of the tile,
+            mbar_init(bar_p_full + 16 * t + 8, 4);    // per half of P
+            mbar_init(bar_o_full + 8 * t, 1);
         }
-        for (int i = 0; i < 4; i++) mbar_init(bar_o_full + 8 * i, 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(bar_sched_full + 8 * i, 1);
+            mbar_init(bar_sched_empty + 8 * i, 9);    // MMA warp + 8 softmax warps
+        }
         fence_mbar_init();
     }
     if (warp == kMmaWarp) {
@@ -263,6 +335,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
+    // Dynamic tile scheduler (replaces the reference's static blockIdx mapping, FA.cu:103-112): the
+    // producer warp claims work indices (first one static, the rest from a global counter) and
+    // publishes them through a 2-slot smem mailbox; every consumer warp reads slot i&1 for its i-th
+    // item.  Work order is heads-outermost, heaviest Q pair first (decode_work), so the causal tail is
+    // made of the lightest items.  Returns -1 when the grid has run out of work.
+    auto next_work = [&](uint32_t i) -> int {
+        const uint32_t slot = i & 1u;
+        mbar_wait(bar_sched_full + 8 * slot, (i >> 1) & 1u, 50);
+        const int w = sched_w[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sched_empty + 8 * slot);
+        return w;
+    };
+
     // The producer and MMA warps run their loops converged (all 32 lanes take the same branches
     // and waits); the instructions with side effects sit under elect_one().  Warp-uniform control
     // flow keeps descriptors and barrier addresses in uniform registers -- in a lane-divergent
@@ -273,10 +359,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (warp == kLoadWarp) {
         // =============================== TMA producer ===============================
         Ring ring{0u, 0u};
-        uint32_t it = 0;
-        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+        for (uint32_t it = 0;; ++it) {
+            // claim the next work item and publish it
+            const uint32_t slot = it & 1u;
+            mbar_wait(bar_sched_empty + 8 * slot, ((it >> 1) & 1u) ^ 1u, 3);
+            int w = 0;
+            if (lane == 0) w = (it == 0) ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(p.sched, 1);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w >= p.total_work) w = -1;
+            if (lane == 0) {
+                sched_w[slot] = w;
+                mbar_arrive(bar_sched_full + 8 * slot);   // release: the slot write is visible to waiters
+            }
+            __syncwarp();
+            if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
-            const int nmax = ((wi.n0 > wi.n1 ? wi.n0 : wi.n1) + 1) >> 1;   // 128-row K/V tiles to stream
+            const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
             const bool have_q1 = wi.q0 + kBlockM < p.Nq;
             mbar_wait(bar_q_empty, (it & 1u) ^ 1u, 1);   // previous item's QK^T MMAs retired
             if (elect_one()) {
@@ -311,100 +409,95 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         Ring rk{0u, 0u};              // ring entry holding K_j
         Ring rv{1u % C::kStages, 0u}; // ring entry holding V_j
         uint32_t it = 0;
+        uint32_t p_phase0 = 0u, p_phase1 = 0u;
         const uint32_t tS0 = tmem_base + C::kTmemS0, tS1 = tmem_base + C::kTmemS1;
         const uint32_t tO0 = tmem_base + C::kTmemO0, tO1 = tmem_base + C::kTmemO1;
         const uint64_t qdesc0 = umma_smem_desc(sQ, 16, 1024);
         const uint64_t qdesc1 = umma_smem_desc(sQ + C::kTileBytes, 16, 1024);
 
-        // S_t[half h] = Q_t K_j[64h..64h+63]^T : N = 64, D/16 k-steps; k-step ks lives in panel ks/4 at
-        // byte offset (ks%4)*32; the K sub-tile starts 64 rows (8192 B) into each panel
-        auto issue_qk = [&](uint32_t tS, uint64_t qdesc, uint32_t k_smem, int h, uint32_t bar) {
-            const uint64_t kdesc = umma_smem_desc(k_smem + h * (kSubN * 128), 16, 1024);
+        // S_t = Q_t K_j^T : D/16 k-steps; k-step ks lives in panel ks/4 at byte offset (ks%4)*32
+        auto issue_qk = [&](uint32_t tS, uint64_t qdesc, uint32_t k_smem, uint32_t bar) {
+            const uint64_t kdesc = umma_smem_desc(k_smem, 16, 1024);
             if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < D / 16; ks++) {
                     const uint64_t off = (uint64_t)(((ks >> 2) * C::kPanelBytes + (ks & 3) * 32) >> 4);
-                    umma_ss(tS + h * kSubN, qdesc + off, kdesc + off, C::kIdescQK, ks > 0 ? 1u : 0u);
+                    umma_ss(tS, qdesc + off, kdesc + off, C::kIdescQK, ks > 0 ? 1u : 0u);
                 }
                 umma_commit(bar);
             }
             __syncwarp();
         };
-        // O_t (+)= P_t[half h] V_j[64h..64h+63] : 4 k-steps of 16 kv rows; P k-step = 8 TMEM columns,
-        // V k-step = 16 rows * 128 B
-        auto issue_pv = [&](uint32_t tO, uint32_t tS, uint32_t v_smem, int h, bool accumulate, uint32_t bar) {
-            const uint64_t vdesc = umma_smem_desc(v_smem + h * (kSubN * 128), C::kPanelBytes, 1024);
-            if (elect_one()) {
+        // O_t (+)= P_t V_j : 8 k-steps of 16 kv rows (P k-step = 8 TMEM columns, V k-step = 16 rows * 128 B),
+        // issued in two halves of 4 k-steps as the two halves of P arrive
+        auto issue_pv = [&](uint32_t tO, uint32_t tP, uint32_t v_smem, bool accumulate, uint32_t bar_p,
+                            uint32_t parity, uint32_t bar_o, int tag) {
+            const uint64_t vdesc = umma_smem_desc(v_smem, C::kPanelBytes, 1024);
 #pragma unroll
-                for (int ks = 0; ks < kSubN / 16; ks++)
-                    umma_ts(tO, tS + h * kSubN + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV,
-                            (accumulate || ks > 0) ? 1u : 0u);
-                umma_commit(bar);
+            for (int h = 0; h < 2; h++) {
+                mbar_wait(bar_p + 8 * h, parity, tag);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 4 * h; ks < 4 * h + 4; ks++)
+                        umma_ts(tO, tP + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV,
+                                (accumulate || ks > 0) ? 1u : 0u);
+                    if (h == 1) umma_commit(bar_o);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         };
         auto commit = [&](uint32_t bar) {
             if (elect_one()) umma_commit(bar);
             __syncwarp();
         };
 
-        uint32_t p_phase = 0u;   // bit (2*t + h): parity of the next P_t[half h] arrival
-        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++it) {
+        for (;; ++it) {
+            const int w = next_work(it);
+            if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
-            const int n0 = wi.n0, n1 = wi.n1;                 // sub-tiles per Q tile
-            const int nsub = n0 > n1 ? n0 : n1;
-            const int ntiles = (nsub + 1) >> 1;
+            const int n0 = wi.n0, n1 = wi.n1;
+            const int nmax = n0 > n1 ? n0 : n1;
             mbar_wait(bar_q_full, it & 1u, 10);
             tc_fence_after();
-            if (ntiles > 0) {
-                // prologue: sub-tiles 0 and 1 of both Q tiles come from K_0
+            if (nmax > 0) {
                 mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 11);
                 tc_fence_after();
                 const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
-                if (0 < n0) issue_qk(tS0, qdesc0, k_smem, 0, bar_s_full + 0);
-                if (0 < n1) issue_qk(tS1, qdesc1, k_smem, 0, bar_s_full + 16);
-                if (1 < n0) issue_qk(tS0, qdesc0, k_smem, 1, bar_s_full + 8);
-                if (1 < n1) issue_qk(tS1, qdesc1, k_smem, 1, bar_s_full + 24);
+                if (n0 > 0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
+                if (n1 > 0) issue_qk(tS1, qdesc1, k_smem, bar_s_full + 8);
                 commit(bar_kv_empty + 8 * rk.idx);
                 rk.advance<C::kStages>(); rk.advance<C::kStages>();
             }
             // Q is free for the next item as soon as the last QK^T of this one has retired
-            if (ntiles <= 1) commit(bar_q_empty);
-            for (int j = 0; j < ntiles; j++) {
-                const bool has_next = j + 1 < ntiles;
+            if (nmax <= 1) commit(bar_q_empty);
+            for (int j = 0; j < nmax; j++) {
+                const bool has_next = j + 1 < nmax;
                 mbar_wait(bar_kv_full + 8 * rv.idx, rv.phase, 12);
                 const uint32_t v_smem = sKV + rv.idx * C::kTileBytes;
-                const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;   // K_{j+1}
+                const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
+                // ---- tile 0: PV0(j), QK0(j+1)
+                if (j < n0) {
+                    issue_pv(tO0, tS0, v_smem, j > 0, bar_p_full, p_phase0, bar_o_full, 13);
+                    p_phase0 ^= 1u;
+                }
                 if (has_next) {
                     mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 15);
                     tc_fence_after();
                 }
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int u = 2 * j + h;
-                    // ---- Q tile 0: PV0(u), QK0(u+2)
-                    if (u < n0) {
-                        mbar_wait(bar_p_full + 8 * h, (p_phase >> h) & 1u, 13);
-                        p_phase ^= 1u << h;
-                        tc_fence_after();
-                        issue_pv(tO0, tS0, v_smem, h, u > 0, bar_o_full + 8 * h);
-                    }
-                    if (u + 2 < n0) issue_qk(tS0, qdesc0, k_smem, h, bar_s_full + 8 * h);
-                    // ---- Q tile 1: PV1(u), QK1(u+2)
-                    if (u < n1) {
-                        mbar_wait(bar_p_full + 16 + 8 * h, (p_phase >> (2 + h)) & 1u, 14);
-                        p_phase ^= 1u << (2 + h);
-                        tc_fence_after();
-                        issue_pv(tO1, tS1, v_smem, h, u > 0, bar_o_full + 16 + 8 * h);
-                    }
-                    if (u + 2 < n1) issue_qk(tS1, qdesc1, k_smem, h, bar_s_full + 16 + 8 * h);
+                if (j + 1 < n0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
+                // ---- tile 1: PV1(j), QK1(j+1)
+                if (j < n1) {
+                    issue_pv(tO1, tS1, v_smem, j > 0, bar_p_full + 16, p_phase1, bar_o_full + 8, 14);
+                    p_phase1 ^= 1u;
                 }
                 commit(bar_kv_empty + 8 * rv.idx);
                 rv.advance<C::kStages>(); rv.advance<C::kStages>();
+                if (j + 1 < n1) issue_qk(tS1, qdesc1, k_smem, bar_s_full + 8);
                 if (has_next) {
                     commit(bar_kv_empty + 8 * rk.idx);
                     rk.advance<C::kStages>(); rk.advance<C::kStages>();
-                    if (j + 2 == ntiles) commit(bar_q_empty);   // K_{ntiles-1} fed the last QK^T of this item
+                    if (j + 2 == nmax) commit(bar_q_empty);   // QK^T(nmax-1) was the last reader of Q
                 }
             }
         }
@@ -417,16 +510,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tmem_base + lane_base + (t ? C::kTmemS1 : C::kTmemS0);
         const uint32_t tO = tmem_base + lane_base + (t ? C::kTmemO1 : C::kTmemO0);
-        const uint32_t my_s_full = bar_s_full + 16 * t;        // + 8 * half
+        const uint32_t my_s_full = bar_s_full + 8 * t;
         const uint32_t my_p_full = bar_p_full + 16 * t;        // + 8 * half
-        const uint32_t my_o_full = bar_o_full + 16 * t;        // + 8 * half
-        uint32_t s_phase = 0;    // bit h: parity of the next S_t[half h] completion
-        // P sub-tiles of parity h handed to the MMA warp so far == completions expected on o_full[t][h].
-        // Two barriers because two PVs can be outstanding at once (sub-tiles u-1 and u): with a single
-        // barrier a parity wait could not tell "both done" from "neither done".
-        uint32_t pv_count[2] = {0u, 0u};
+        const uint32_t my_o_full = bar_o_full + 8 * t;
+        uint32_t s_phase = 0;
+        uint32_t pv_count = 0;   // P tiles handed to the MMA warp so far == o_full completions expected
 
-        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        for (uint32_t it = 0;; ++it) {
+            const int w = next_work(it);
+            if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
             const int q_start = wi.q0 + t * kBlockM;
             if (q_start >= p.Nq) continue;                     // this Q tile does not exist
@@ -439,39 +531,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const int lim = (int)lim_ll;
 
             float m_ref = -INFINITY, l_run = 0.f;
-#pragma unroll 1
-            for (int u0 = 0; u0 < n_t; u0 += 2) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int u = u0 + h;
-                    if (u < n_t) {
-                        mbar_wait(my_s_full + 8 * h, (s_phase >> h) & 1u, 20 + t);
-                        s_phase ^= 1u << h;
-                        tc_fence_after();
-                        const int k0 = u * kSubN;
-                        const bool need_mask =
-                            (k0 + kSubN > p.Nkv) || (p.causal && k0 + kSubN - 1 > q_start + p.shift);
-                        // a rescale at sub-tile u waits for PV(u-1): parity 1-h
-                        if (need_mask)
-                            softmax_subtile<D, true>(p, tS + h * kSubN, tO, my_p_full + 8 * h, my_o_full + 8 * (1 - h),
-                                                     lim - k0, u > 0, pv_count[1 - h], m_ref, l_run);
-                        else
-                            softmax_subtile<D, false>(p, tS + h * kSubN, tO, my_p_full + 8 * h, my_o_full + 8 * (1 - h),
-                                                      kSubN, u > 0, pv_count[1 - h], m_ref, l_run);
-                        ++pv_count[h];
-                    }
-                }
+            for (int j = 0; j < n_t; j++) {
+                mbar_wait(my_s_full, s_phase, 20 + t);
+                s_phase ^= 1u;
+                tc_fence_after();
+                const int k0 = j * kBlockN;
+                const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
+                if (need_mask)
+                    softmax_tile<D, true>(p, tS, tO, my_p_full, my_o_full, lim - k0, j > 0, pv_count, m_ref, l_run);
+                else
+                    softmax_tile<D, false>(p, tS, tO, my_p_full, my_o_full, kBlockN, j > 0, pv_count, m_ref, l_run);
+                ++pv_count;
             }
 
             // ---- epilogue: O_t / l -> fp16 -> global (or the partial-state format) ----
-            // the last PV of each parity (sub-tiles n_t-1 and n_t-2) must have retired
-            if (n_t > 1) {
-                const int h2 = n_t & 1;              // parity of sub-tile n_t - 2
-                mbar_wait(my_o_full + 8 * h2, (pv_count[h2] - 1u) & 1u, 30 + t);
-            }
             if (n_t > 0) {
-                const int h1 = (n_t - 1) & 1;
-                mbar_wait(my_o_full + 8 * h1, (pv_count[h1] - 1u) & 1u, 32 + t);
+                mbar_wait(my_o_full, (pv_count - 1u) & 1u, 30 + t);
                 tc_fence_after();
             }
             const bool row_ok = row < p.Nq;
@@ -560,6 +635,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) {
+        // last CTA out re-arms the scheduler state for the launch that reuses this slot
+        __threadfence();
+        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
+        }
+    }
     if (warp == kMmaWarp) {
         __syncwarp();
         tc_fence_after();

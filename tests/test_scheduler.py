@@ -31,21 +31,41 @@ def test_every_q_tile_exactly_once(N, causal):
                 assert (it["bh"], q_start) not in seen
                 seen.add((it["bh"], q_start))
                 last_row = min(q_start + 127, N - 1)
-                # trip counts are in 64-wide KV sub-tiles (fa::kSubN)
-                want = (min(N, last_row + 1) + 63) // 64 if causal else (N + 63) // 64
+                want = (min(N, last_row + 1) + 127) // 128 if causal else (N + 127) // 128
                 assert n == want, (it, t)
             else:
                 assert n == 0
     assert len(seen) == B * H * nq_tiles
 
 
-def test_heavy_first_within_head_and_heads_outermost():
-    its = items(1, 4, 2048, 2048, 128, True)
-    bhs = [it["bh"] for it in its]
-    assert bhs == sorted(bhs)
-    for bh in range(4):
-        w = [it["n1"] + it["n0"] for it in its if it["bh"] == bh]
+def test_heavy_first_within_l2_sized_head_groups():
+    # N=8192 D=128: K+V of a head = 4 MB -> 16 heads per group; inside a group heavy-first across heads
+    its = items(1, 32, 8192, 8192, 128, True)
+    nqp = 32
+    per_group = 16 * nqp
+    assert len(its) == 32 * nqp
+    for g in range(2):
+        grp = its[g * per_group:(g + 1) * per_group]
+        assert {it["bh"] for it in grp} == set(range(16 * g, 16 * g + 16))
+        w = [it["n0"] + it["n1"] for it in grp]
         assert w == sorted(w, reverse=True)
+    # the launch ends with the lightest items
+    assert its[-1]["n0"] + its[-1]["n1"] == min(it["n0"] + it["n1"] for it in its)
+
+
+def test_short_sequences_form_one_group():
+    its = items(1, 4, 2048, 2048, 128, True)
+    w = [it["n0"] + it["n1"] for it in its]
+    assert w == sorted(w, reverse=True)          # pure heavy-first: all heads fit one group
+    assert [it["bh"] for it in its[:4]] == [0, 1, 2, 3]
+
+
+def test_last_group_may_be_smaller():
+    # 5 heads of 16 MB K/V each (N=32768): groups of 4 + 1, every (head, pair) still exactly once
+    its = items(1, 5, 32768, 32768, 128, True)
+    seen = {(it["bh"], it["q0"]) for it in its}
+    assert len(seen) == len(its) == 5 * 128
+    assert [it["bh"] for it in its[:4]] == [0, 1, 2, 3] and its[4 * 128]["bh"] == 4
 
 
 def test_masked_tiles_skipped_with_offsets():
@@ -54,12 +74,12 @@ def test_masked_tiles_skipped_with_offsets():
     assert all(it["n0"] == 0 and it["n1"] == 0 for it in its)
     # block entirely in the past: every tile needs all KV tiles, as in non-causal
     its = items(1, 1, 512, 512, 128, True, shift=512)
-    assert all(it["n0"] == 8 and it["n1"] == 8 for it in its)
+    assert all(it["n0"] == 4 and it["n1"] == 4 for it in its)
 
 
 def test_total_causal_tiles_is_triangular():
     N = 8192
     its = items(1, 1, N, N, 128, True)
     tiles = sum(it["n0"] + it["n1"] for it in its)
-    n = N // 128          # q tiles; q tile i needs 2*(i+1) sub-tiles of 64 keys
-    assert tiles == n * (n + 1)
+    n = N // 128
+    assert tiles == n * (n + 1) // 2
