@@ -29,20 +29,32 @@ def check(B, H, N, D, causal, dist):
     return ok, mx, mean
 
 
-def tflops(B, H, N, D, causal, iters=30, warm=5):
+import pynvml
+pynvml.nvmlInit()
+_h = pynvml.nvmlDeviceGetHandleByIndex(0)
+CLOCKS = []
+
+
+def tflops(B, H, N, D, causal, iters=None, warm=5, target_ms=150.0):
+    """Times enough back-to-back launches to cover ~target_ms (steady clocks), returns TFLOPS and
+    records the SM clock NVML reports right after the timed loop."""
     g = torch.Generator(device="cuda").manual_seed(0)
     q, k, v = ((torch.rand((B, H, N, D), device="cuda", generator=g) - 0.5).half() for _ in range(3))
     o = torch.empty_like(q)
+    fl = 4.0 * B * H * N * N * D / (2 if causal else 1)
     for _ in range(warm):
         fa.flash_attn_fwd(q, k, v, causal=bool(causal), out=o)
+    if iters is None:
+        iters = int(max(10, min(2000, target_ms / (fl / 1.0e12 * 1e-3 * 1e3 / 1.0))))   # assume ~1 PFLOP/s
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
         fa.flash_attn_fwd(q, k, v, causal=bool(causal), out=o)
     e1.record()
+    CLOCKS.append(pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM))
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    return 4.0 * B * H * N * N * D / (2 if causal else 1) / ms / 1e9
+    return fl / ms / 1e9
 
 
 print("lib:", fa.LIB_PATH)
@@ -56,5 +68,6 @@ print("watchdog:", wd)
 seqs = (2048, 8192) if quick else (512, 1024, 2048, 4096, 8192, 16384)
 for causal in (0, 1):
     print("causal" if causal else "full  ", " ".join(f"N{n}:{tflops(1, 32, n, 128, causal):7.1f}" for n in seqs))
-print("d64 B32 H16 N2048 full:", f"{tflops(32, 16, 2048, 64, 0):7.1f}", "| cfg3-like B4 H32 N8192 causal:", f"{tflops(4, 32, 8192, 128, 1, 10, 2):7.1f}")
+print("SM clock (MHz) sampled during each timed loop:", CLOCKS)
+print("d64 B32 H16 N2048 full:", f"{tflops(32, 16, 2048, 64, 0):7.1f}", "| cfg3-like B4 H32 N8192 causal:", f"{tflops(4, 32, 8192, 128, 1):7.1f}")
 sys.exit(1 if bad or wd["aborted"] else 0)
