@@ -43,6 +43,7 @@ WORKLOADS = {
     "cfg2_n16384_full": (1, 32, 16384, 128, 0),
     "cfg3_b16_n8192_causal": (16, 32, 8192, 128, 1),     # configs[2] (strong scaling: B*H sharded)
     "cfg4_d64_n2048_full": (32, 16, 2048, 64, 0),        # configs[3]
+    "cfg5_ring_n131072_causal": (1, 32, 131072, 128, 1),  # configs[4]: ring context parallel over the ranks
 }
 DEFAULT_WORKLOAD = "cfg2_n8192_causal"
 NOMINAL_FP16_TFLOPS = 2250.0
@@ -153,6 +154,62 @@ def cpu_baseline(workload, budget_rows=None):
                       f"causal={causal}), {row_flops / 1e9:.1f} GFLOP in {dt:.1f} s; oracle/attn_oracle.c, pthreads"}
 
 
+def bench_ring(args, workload, rank, world, local_rank, barrier):
+    """Config 5: causal N=131072 with ring context parallelism (K/V chunk pairs rotate over NCCL
+    send/recv, overlapped with compute).  world == 1 runs the monolithic kernel as the baseline."""
+    import torch
+    import torch.distributed as dist
+    import flash_attention_cuda_b200 as fa
+    from flash_attention_cuda_b200 import ring
+    B, H, N, D, causal = workload
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    C = N // (2 * world)
+
+    def mk(n):
+        return (torch.rand((B, H, n, D), device="cuda", generator=g) - 0.5).half()
+
+    if world == 1:
+        q, k, v = mk(N), mk(N), mk(N)
+        o = torch.empty_like(q)
+        step = lambda: fa.flash_attn_fwd(q, k, v, causal=bool(causal), out=o)
+    else:
+        q, k, v = ([mk(C), mk(C)] for _ in range(3))
+        step = lambda: ring.ring_attention_forward(q, k, v, bool(causal))
+    steps, warm = max(2, min(args.steps, 5)), 2
+    for _ in range(warm):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        fl = flops(B, H, N, D, causal)
+        pk = peaks()
+        print(json.dumps({
+            "metric": "fwd_tflops", "value": round(fl / (ms * 1e-3) / 1e12, 2), "unit": "TFLOPS", "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": round(ms, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": args.workload, "B": B, "H": H, "N": N, "D": D, "causal": causal,
+                       "parallelism": f"ring-cp{world} zig-zag, NCCL send/recv of K/V chunk pairs "
+                                      f"({4 * B * H * C * D * 2 / 2**20:.0f} MiB per hop per rank)" if world > 1
+                       else "single GPU, monolithic kernel"},
+            "roofline": {"bound": "tensor", "achieved": round(fl / (ms * 1e-3) / 1e12 / world, 2),
+                         "peak": pk["tflops_sustained"] or pk["tflops"], "unit": "TFLOP/s",
+                         "frac": round(fl / (ms * 1e-3) / 1e12 / world / (pk["tflops_sustained"] or pk["tflops"]), 4),
+                         "traffic": None, "peak_source": pk["source"] + ", cuBLAS bf16 sustained (long step)"},
+            "gpu_launches": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -232,6 +289,14 @@ def main():
 
     stream = torch.cuda.current_stream()
     sp = ctypes.c_void_p(stream.cuda_stream)
+
+    if args.workload.startswith("cfg5_ring"):
+        return bench_ring(args, workload, rank, world, local_rank, barrier)
+    if args.workload.startswith("cfg3") and world > 1:
+        # strong scaling: the B*H heads are split across ranks (no collective), total work fixed
+        from flash_attention_cuda_b200.ring import bh_shard
+        _, cnt = bh_shard(B * H, rank, world)
+        B, H = 1, cnt
 
     def make_inputs(b, h, n, d, seed):
         g = torch.Generator(device="cuda").manual_seed(seed + 1000 * rank)
@@ -320,9 +385,12 @@ def main():
     out = {
         "metric": "fwd_tflops", "value": round(value, 2), "unit": "TFLOPS", "n_gpus": n_gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "scaling": "strong" if (args.workload.startswith("cfg3") and world > 1) else "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": args.workload, "B": B, "H": H, "N": N, "D": D, "causal": causal,
-                   "per_gpu": "every rank runs the full workload on its own GPU (batch x heads shard, no collective)",
+                   "per_gpu": "every rank runs the full workload on its own GPU (batch x heads shard, no collective)"
+                              if not (args.workload.startswith("cfg3") and world > 1) else
+                              "the workload's B*H heads are split across the ranks (no collective); B,H here are rank 0's share",
                    "l2": f"inputs {4 * nbytes / 2**20:.0f} MiB per step > 126 MB L2 (no flush needed)"
                          if 4 * nbytes > 126e6 else "inputs fit L2: hot-L2 timing, reference method (FA.cu:942-960)",
                    "flops_convention": "4*B*H*N^2*D, /2 causal (FA.cu:938-939)"},

@@ -1,0 +1,120 @@
+"""Multi-GPU drivers for the forward path: one process per GPU over torch.distributed.
+
+* batch x heads sharding (config 3): every (b, h) is an independent problem (reference
+  flash_attention.cu:120-122), so ranks take contiguous slices of B*H and never communicate.
+* ring context parallelism (config 5): the sequence is cut into 2P chunks, rank r owns chunks r and
+  2P-1-r (zig-zag: every hop costs every rank exactly two unmasked chunk pairs under a causal mask);
+  Q and the partial state stay, K/V chunk pairs travel around the ring with send/recv on a side
+  stream while the current pair is being consumed.  Per-hop math is `flash_attn_fwd_ex`, which
+  accumulates (O un-normalised fp32, m, l) in place with the merge algebra of the reference's split-K
+  code (flash_attention.cu:460-496, 575-597); `flash_attn_finalize` writes O = o_partial / l.
+
+The compute callables are injectable so the schedule and the send/recv plumbing can be exercised on CPU
+with gloo (tests/test_ring_cpu.py); the defaults are the CUDA library and nothing else.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+
+def bh_shard(total_bh: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [start, start+count) of the B*H independent heads for `rank`."""
+    base, rem = divmod(total_bh, world)
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+def zigzag_chunks(rank: int, world: int) -> Tuple[int, int]:
+    """Chunk ids (of 2*world equal chunks) owned by `rank`: (r, 2P-1-r)."""
+    return rank, 2 * world - 1 - rank
+
+
+def hop_pairs(rank: int, src: int, world: int, causal: bool) -> List[Tuple[int, int, bool]]:
+    """(q chunk slot, kv chunk slot, needs_diagonal_mask) pairs rank must compute while it holds
+    src's K/V.  Slot 0 = the rank's low chunk, slot 1 = its high chunk.  Fully masked pairs are
+    dropped here, on the host, so they cost nothing."""
+    qa = zigzag_chunks(rank, world)
+    kb = zigzag_chunks(src, world)
+    out = []
+    for qi, a in enumerate(qa):
+        for ki, b in enumerate(kb):
+            if not causal:
+                out.append((qi, ki, False))
+            elif b < a:
+                out.append((qi, ki, False))      # K/V chunk entirely in the past: no mask
+            elif b == a:
+                out.append((qi, ki, True))       # diagonal chunk: causal mask inside
+    return out
+
+
+def _cuda_partial(q, k, v, o_partial, ml, causal, q_offset, kv_offset, accumulate):
+    from . import flash_attn_fwd_partial
+    flash_attn_fwd_partial(q, k, v, o_partial, ml, causal, q_offset, kv_offset, accumulate)
+
+
+def _cuda_finalize(o_partial, ml, out):
+    from . import flash_attn_finalize
+    flash_attn_finalize(o_partial, ml, out)
+
+
+def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, group=None, *,
+                           partial: Optional[Callable] = None, finalize: Optional[Callable] = None,
+                           comm_stream=None):
+    """Ring-CP forward.  q, k, v: pairs (low chunk, high chunk) of contiguous [B, H, C, D] tensors in the
+    zig-zag layout of `zigzag_chunks`.  Returns the pair of output chunks, same layout as q.
+
+    Each hop: post isend/irecv of the K/V pair for the next hop, run the (at most four, causal: two)
+    chunk-pair kernels of this hop, wait for the transfer, swap buffers."""
+    import torch
+    import torch.distributed as dist
+
+    partial = partial or _cuda_partial
+    finalize = finalize or _cuda_finalize
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    B, H, C, D = q[0].shape
+    dev = q[0].device
+    on_cuda = dev.type == "cuda"
+
+    o_part = [torch.zeros((B * H * C, D), dtype=torch.float32, device=dev) for _ in range(2)]
+    ml = [torch.zeros((B * H * C, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+    started = [False, False]
+
+    cur = [k[0], k[1], v[0], v[1]]
+    nxt = [torch.empty_like(t) for t in cur] if world > 1 else None
+    send_to = (rank + 1) % world
+    recv_from = (rank - 1) % world
+    if on_cuda and comm_stream is None and world > 1:
+        comm_stream = torch.cuda.Stream(device=dev)
+
+    qa = zigzag_chunks(rank, world)
+    for hop in range(world):
+        src = (rank - hop) % world
+        reqs = []
+        if hop + 1 < world:
+            ops = []
+            for t_send, t_recv in zip(cur, nxt):
+                ops.append(dist.P2POp(dist.isend, t_send, send_to, group))
+                ops.append(dist.P2POp(dist.irecv, t_recv, recv_from, group))
+            if on_cuda:
+                comm_stream.wait_stream(torch.cuda.current_stream(dev))   # cur is ready to be read
+                with torch.cuda.stream(comm_stream):
+                    reqs = dist.batch_isend_irecv(ops)
+            else:
+                reqs = dist.batch_isend_irecv(ops)
+        kb = zigzag_chunks(src, world)
+        for qi, ki, diag in hop_pairs(rank, src, world, causal):
+            partial(q[qi], cur[ki], cur[2 + ki], o_part[qi], ml[qi], bool(diag),
+                    qa[qi] * C, kb[ki] * C, started[qi])
+            started[qi] = True
+        if hop + 1 < world:
+            for r in reqs:
+                r.wait()
+            if on_cuda:
+                torch.cuda.current_stream(dev).wait_stream(comm_stream)
+                comm_stream.wait_stream(torch.cuda.current_stream(dev))   # kernels that read cur are ordered first
+            cur, nxt = nxt, cur
+    out = [torch.empty_like(q[0]), torch.empty_like(q[1])]
+    for i in range(2):
+        finalize(o_part[i], ml[i], out[i])
+    return out

@@ -1,0 +1,52 @@
+"""Multi-GPU numerical check of ring context parallelism (run under torchrun on >= 2 GPUs):
+the ring result must equal the monolithic single-kernel result on the same global tensors, and both are
+spot-checked against the CPU oracle on sampled rows.
+   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/harness/ring_check.py [N]"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import _oracle  # noqa: E402
+import flash_attention_cuda_b200 as fa  # noqa: E402
+from flash_attention_cuda_b200 import ring  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+B, H, D = 1, 4, 128
+g = torch.Generator(device="cuda").manual_seed(99)          # identical global tensors on every rank
+q, k = (torch.randn((B, H, N, D), device="cuda", generator=g).half() for _ in range(2))
+v = (torch.randn((B, H, N, D), device="cuda", generator=g) * 0.5).half()
+ok = True
+for causal in (True, False):
+    full = fa.flash_attn_fwd(q, k, v, causal=causal)
+    C = N // (2 * world)
+    lo, hi = ring.zigzag_chunks(rank, world)
+    ch = lambda x: [x[:, :, c * C:(c + 1) * C].contiguous() for c in (lo, hi)]
+    out = ring.ring_attention_forward(ch(q), ch(k), ch(v), causal)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for o, c in zip(out, (lo, hi)):
+        worst = max(worst, (o.float() - full[:, :, c * C:(c + 1) * C].float()).abs().max().item())
+    # oracle on a few rows of this rank's chunks
+    rows = np.array([lo * C, lo * C + C - 1, hi * C, hi * C + C // 2, hi * C + C - 1], np.int32)
+    bhs = np.array([0, 1, 2, 3, 0], np.int32)
+    ref = _oracle.attention_rows(q.cpu().numpy(), k.cpu().numpy(), v.cpu().numpy(), causal, bhs, rows)
+    got = torch.stack([out[0 if r < (lo + 1) * C and r >= lo * C else 1][0, b, r - (lo * C if lo * C <= r < (lo + 1) * C else hi * C)]
+                       for b, r in zip(bhs, rows)]).cpu().numpy()
+    mx, mean = _oracle.diff(got, ref)
+    good = worst <= 2e-3 and mx <= 2e-3 and mean <= 2e-4
+    ok &= good
+    print(f"rank {rank} causal={causal}: ring vs monolithic max|diff|={worst:.2e}; ring vs oracle rows max={mx:.2e} mean={mean:.2e} "
+          f"{'PASS' if good else 'FAIL'}", flush=True)
+t = torch.tensor([0 if ok else 1], device="cuda")
+dist.all_reduce(t)
+dist.destroy_process_group()
+sys.exit(int(t.item() != 0))

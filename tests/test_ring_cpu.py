@@ -1,0 +1,139 @@
+"""CPU-only, world_size 2 over gloo: the multi-GPU host logic of flash_attention_cuda_b200/ring.py.
+
+The ring driver is run for real (zig-zag ownership, hop schedule, double-buffered send/recv of K/V
+chunk pairs, in-place accumulation of partial states, finalize); only the per-hop math is injected as a
+numpy stand-in with the semantics of flash_attn_fwd_ex, so this needs no GPU.  The result is gated
+against the monolithic CPU oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import _oracle
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+from flash_attention_cuda_b200 import ring  # noqa: E402
+
+FLT_MAX = np.finfo(np.float32).max
+
+
+def np_partial(q, k, v, o_part, ml, causal, q_off, kv_off, accumulate):
+    """numpy stand-in for flash_attn_fwd_ex: partial state (O un-normalised, m, l), FA.cu:460-496 format,
+    merged in place with the algebra of FA.cu:575-597 when `accumulate`."""
+    B, H, C, D = q.shape
+    Ck = k.shape[2]
+    qf, kf, vf = (t.float().numpy().reshape(B * H, -1, D) for t in (q, k, v))
+    scale = np.float32(1.0 / np.sqrt(D))
+    rows = np.arange(C)[:, None] + q_off
+    cols = np.arange(Ck)[None, :] + kv_off
+    for bh in range(B * H):
+        s = (qf[bh] @ kf[bh].T) * scale
+        if causal:
+            s = np.where(cols <= rows, s, -np.inf)
+        m = s.max(axis=1)
+        m_safe = np.where(np.isinf(m), 0.0, m)
+        p = np.exp(s - m_safe[:, None])
+        l_new = p.sum(axis=1).astype(np.float32)
+        o_new = (p.astype(np.float16).astype(np.float32) @ vf[bh]).astype(np.float32)
+        m_new = np.where(np.isinf(m), -FLT_MAX, m).astype(np.float32)
+        sl = slice(bh * C, (bh + 1) * C)
+        op = o_part[sl].numpy()
+        mlv = ml[sl].numpy()
+        if accumulate:
+            m_old, l_old = mlv[:, 0].copy(), mlv[:, 1].copy()
+            m_max = np.maximum(m_old, m_new)
+            w_old = np.where(m_old <= -FLT_MAX, 0.0, np.exp(m_old - m_max)).astype(np.float32)
+            w_new = np.where(m_new <= -FLT_MAX, 0.0, np.exp(m_new - m_max)).astype(np.float32)
+            op[:] = op * w_old[:, None] + o_new * w_new[:, None]
+            mlv[:, 0] = m_max
+            mlv[:, 1] = l_old * w_old + l_new * w_new
+        else:
+            op[:] = o_new
+            mlv[:, 0] = m_new
+            mlv[:, 1] = l_new
+
+
+def np_finalize(o_part, ml, out):
+    l = ml[:, 1:2]
+    res = torch.where(l > 0, o_part / l, torch.zeros_like(o_part))
+    out.copy_(res.reshape(out.shape).half())
+
+
+def _worker(rank, world, port, causal, N, D, H, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)     # same global tensors on every rank
+        q, k, v = (rng.standard_normal((1, H, N, D), dtype=np.float32).astype(np.float16) for _ in range(3))
+        v = (v.astype(np.float32) * 0.5).astype(np.float16)
+        C = N // (2 * world)
+        lo, hi = ring.zigzag_chunks(rank, world)
+
+        def chunks(x):
+            t = torch.from_numpy(x)
+            return [t[:, :, c * C:(c + 1) * C].contiguous() for c in (lo, hi)]
+
+        out = ring.ring_attention_forward(chunks(q), chunks(k), chunks(v), causal,
+                                          partial=np_partial, finalize=np_finalize)
+        ref = _oracle.attention(q, k, v, causal)
+        worst = (0.0, 0.0)
+        for o, c in zip(out, (lo, hi)):
+            mx, mean = _oracle.diff(o.numpy(), ref[:, :, c * C:(c + 1) * C])
+            worst = (max(worst[0], mx), max(worst[1], mean))
+        ret[rank] = worst
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("causal", [True, False])
+def test_ring_cp_two_ranks_gloo(causal):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), causal, 128, 64, 2, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        mx, mean = ret[r]
+        assert mx <= 2e-3 and mean <= 2e-4, (r, mx, mean)
+
+
+def test_zigzag_hop_schedule_is_balanced_and_complete():
+    for world in (2, 4, 8):
+        covered = set()
+        for rank in range(world):
+            qa = ring.zigzag_chunks(rank, world)
+            for hop in range(world):
+                src = (rank - hop) % world
+                kb = ring.zigzag_chunks(src, world)
+                pairs = ring.hop_pairs(rank, src, world, causal=True)
+                # every hop costs every rank two chunk pairs (diagonal pairs count half each)
+                cost = sum(0.5 if d else 1.0 for _, _, d in pairs)
+                assert cost == (2.0 if hop else 2.0), (world, rank, hop, pairs)
+                for qi, ki, d in pairs:
+                    covered.add((qa[qi], kb[ki]))
+                    assert (qa[qi] == kb[ki]) == d
+        n = 2 * world
+        assert covered == {(a, b) for a in range(n) for b in range(n) if b <= a}
+
+
+def test_bh_shard_partitions_heads():
+    for total, world in [(512, 8), (512, 4), (32, 8), (10, 4), (3, 8)]:
+        spans = [ring.bh_shard(total, r, world) for r in range(world)]
+        assert sum(c for _, c in spans) == total
+        pos = 0
+        for s, c in spans:
+            assert s == pos
+            pos += c
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
