@@ -1,0 +1,50 @@
+"""Per-tile softmax timing of a -DFA_TIMING build: cycles a softmax warp waits for S vs cycles from
+S-ready to P-arrive.   FLASH_ATTN_B200_LIB=build/libfa_t1.so python tests/harness/timing.py [N] [causal]"""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import flash_attention_cuda_b200 as fa  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+causal = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
+L = fa.lib()
+L.flash_attn_debug_timing.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+buf = (ctypes.c_ulonglong * 32)()
+g = torch.Generator(device="cuda").manual_seed(0)
+q, k, v = ((torch.rand((1, 32, N, 128), device="cuda", generator=g) - 0.5).half() for _ in range(3))
+o = torch.empty_like(q)
+for _ in range(3):
+    fa.flash_attn_fwd(q, k, v, causal=causal, out=o)
+L.flash_attn_debug_timing(buf, 1)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    fa.flash_attn_fwd(q, k, v, causal=causal, out=o)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+L.flash_attn_debug_timing(buf, 0)
+fl = 4.0 * 32 * N * N * 128 / (2 if causal else 1)
+print(f"{os.path.basename(fa.LIB_PATH)} N={N} causal={causal}: {fl / ms / 1e9:.1f} TFLOPS")
+for t in range(2):
+    for h in range(2):
+        w, b, n = (buf[(t * 2 + h) * 3 + i] for i in range(3))
+        if n:
+            print(f"  tile {t} half {h}: wait-for-S {w / n:7.1f} cyc  S->P {b / n:7.1f} cyc  period {(w + b) / n:7.1f}  ({n} tiles)")
+c, ns, n = buf[20], buf[21], buf[22]
+if n:
+    print(f"  CTA lifetime: {c / n:.0f} cycles = {ns / n / 1e3:.1f} us -> SM clock {c / ns * 1e3:.0f} MHz; launches x CTAs = {n}; kernel {ms * 1e3:.1f} us")
+a, b, c2, n2 = buf[16], buf[17], buf[18], buf[19]
+if n2:
+    print(f"  per item (tile 0): wait first S {a / n2:.0f} cyc, tile loop {b / n2:.0f} cyc, epilogue {c2 / n2:.0f} cyc ({n2} items)")
+if buf[25]:
+    print(f"  pair-barrier wait: first tile {buf[24] / buf[25]:.0f} cyc, other tiles {buf[26] / max(1, buf[27]):.0f} cyc")
+if buf[25]:
+    print(f"  first tile: pass1 {buf[28] / buf[25]:.0f} cyc, whole softmax_tile {buf[29] / buf[25]:.0f} cyc; other tiles whole {buf[30] / max(1, buf[27]):.0f} cyc")
+if buf[14]:
+    n3 = buf[14]
+    print(f"  MMA warp per KV tile: wait V_j {buf[12] / n3:.0f} cyc, wait K_j+1 {buf[13] / n3:.0f} cyc, wait P halves (4 per tile) {buf[15] / n3:.0f} cyc total")
