@@ -134,7 +134,21 @@ int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const 
     int grid = p.total_work < st->num_sms ? p.total_work : st->num_sms;
     if (grid < 1) grid = 1;
     p.sched = st->sched + 2 * (st->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
-    fa::fa_fwd_kernel<D><<<grid, fa::kNumThreads, fa::Cfg<D>::kSmemBytes, stream>>>(tq, tk, tv, p);
+    // launched with programmatic stream serialization (PDL): the kernel's prologue overlaps the tail
+    // of its predecessor in the stream; it executes griddepcontrol.wait before touching global memory
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(fa::kNumThreads);
+    cfg.dynamicSmemBytes = fa::Cfg<D>::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D>, tq, tk, tv, p);
+    if (le != cudaSuccess) return (int)le;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();   // FA.cu:662
 }
@@ -301,6 +315,21 @@ extern "C" int flash_attn_debug_status(unsigned int* out4) {
     if (e != cudaSuccess) return (int)e;
     return (int)cudaMemcpyFromSymbol(out4, sm100::g_watchdog, 4 * sizeof(unsigned int));
 }
+
+#ifdef FA_TIMING
+// debug builds only (-DFA_TIMING): in-kernel clock64 probes, see tests/harness/timing.py
+extern "C" int flash_attn_debug_timing(unsigned long long* out32, int reset) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyFromSymbol(out32, fa::g_timing, 32 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return (int)e;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        e = cudaMemcpyToSymbol(fa::g_timing, z, sizeof z);
+    }
+    return (int)e;
+}
+#endif
 
 // Host-side mirror of the device work decomposition, exported for the scheduler tests
 // (every (bh, q-tile) exactly once, heavy-first, masked tiles skipped).

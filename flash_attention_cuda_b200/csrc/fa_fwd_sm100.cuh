@@ -129,6 +129,10 @@ __host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
     return it;
 }
 
+#ifdef FA_TIMING
+__device__ unsigned long long g_timing[32];
+#endif
+
 struct Ring {
     uint32_t idx, phase;
     template <int kStages>
@@ -181,8 +185,12 @@ __device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64
             const uint64_t x2 =
                 fma_f32x2(pack_f32x2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, neg2);
             float p0, p1;
+#ifdef FA_SKELETON
+            unpack_f32x2(x2, p0, p1);
+#else
             if (q < kPolyPairs) exp2_pair<true>(x2, p0, p1);
             else exp2_pair<false>(x2, p0, p1);
+#endif
             if (q & 1) sum_b = add_f32x2(sum_b, pack_f32x2(p0, p1));   // row sum of the un-rounded p (FA.cu:273-279)
             else sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
             __half2 h = __floats2half2_rn(p0, p1);                     // low half = even column
@@ -301,6 +309,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+#ifdef FA_TIMING
+    long long k_c0 = 0;
+    unsigned long long k_t0 = 0;
+    if (threadIdx.x == 0) {
+        k_c0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_t0));
+    }
+#endif
 
     if (threadIdx.x == 0) {
         mbar_init(bar_q_full, 1);
@@ -334,6 +350,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+    // prefetch) may overlap the tail of the previous kernel in the stream; global memory is only
+    // touched below this point.  The next kernel's prologue may start as soon as our CTAs retire.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // Dynamic tile scheduler (replaces the reference's static blockIdx mapping, FA.cu:103-112): the
     // producer warp claims work indices (first one static, the rest from a global counter) and
@@ -532,9 +554,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
             float m_ref = -INFINITY, l_run = 0.f;
             for (int j = 0; j < n_t; j++) {
+#ifdef FA_TIMING
+                const long long tw0 = clock64();
+#endif
                 mbar_wait(my_s_full, s_phase, 20 + t);
                 s_phase ^= 1u;
                 tc_fence_after();
+#ifdef FA_TIMING
+                const long long tw1 = clock64();
+#endif
                 const int k0 = j * kBlockN;
                 const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
                 if (need_mask)
@@ -542,6 +570,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 else
                     softmax_tile<D, false>(p, tS, tO, my_p_full, my_o_full, kBlockN, j > 0, pv_count, m_ref, l_run);
                 ++pv_count;
+#ifdef FA_TIMING
+                if (lane == 0 && (warp & 3) == 0 && j > 0 && (j & 7) == 0) {   // sampled: 1 tile in 8
+                    const long long tw2 = clock64();
+                    atomicAdd(&g_timing[t * 3 + 0], (unsigned long long)(tw1 - tw0));
+                    atomicAdd(&g_timing[t * 3 + 1], (unsigned long long)(tw2 - tw1));
+                    atomicAdd(&g_timing[t * 3 + 2], 1ull);
+                }
+#endif
             }
 
             // ---- epilogue: O_t / l -> fp16 -> global (or the partial-state format) ----
@@ -635,6 +671,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
+#ifdef FA_TIMING
+    if (threadIdx.x == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        atomicAdd(&g_timing[20], (unsigned long long)(clock64() - k_c0));   // CTA lifetime, SM cycles
+        atomicAdd(&g_timing[21], t1 - k_t0);                                // CTA lifetime, ns
+        atomicAdd(&g_timing[22], 1ull);
+    }
+#endif
     if (threadIdx.x == 0) {
         // last CTA out re-arms the scheduler state for the launch that reuses this slot
         __threadfence();

@@ -264,7 +264,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_maj
 // ------------------------------------------------------------------ math
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
+#ifdef FA_NO_EXP
+    y = x;
+#else
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+#endif
     return y;
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {   // FMNMX3

@@ -175,9 +175,11 @@ static void bench_row(const Shape& s, bool with_v9, bool quick) {
             s9 += v9[r];
         }
     }
-    printf("%-6d  %-5d  %7.1f %7.1f %7.1f  %7.1f  %5.1f%%  %5.1f%%   %7.2f  %6.1fx\n", s.N, s.H, ours[0], ours[1],
-           ours[2], so / runs, 100.0 * so / runs / 2250.0, 100.0 * so / runs / 1671.4, s9 / runs,
-           s9 > 0 ? so / s9 : 0.0);
+    char r2[16] = "      -", r3[16] = "      -";
+    if (runs > 1) snprintf(r2, sizeof r2, "%7.1f", ours[1]);
+    if (runs > 2) snprintf(r3, sizeof r3, "%7.1f", ours[2]);
+    printf("%-6d  %-5d  %7.1f %s %s  %7.1f  %5.1f%%  %5.1f%%   %7.2f  %6.1fx\n", s.N, s.H, ours[0], r2, r3, so / runs,
+           100.0 * so / runs / 2250.0, 100.0 * so / runs / 1671.4, s9 / runs, s9 > 0 ? so / s9 : 0.0);
     free(hQ); free(hK); free(hV);
     CUDA_CHECK(cudaFree(dQ)); CUDA_CHECK(cudaFree(dK)); CUDA_CHECK(cudaFree(dV)); CUDA_CHECK(cudaFree(dO));
 }

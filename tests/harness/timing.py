@@ -31,20 +31,9 @@ L.flash_attn_debug_timing(buf, 0)
 fl = 4.0 * 32 * N * N * 128 / (2 if causal else 1)
 print(f"{os.path.basename(fa.LIB_PATH)} N={N} causal={causal}: {fl / ms / 1e9:.1f} TFLOPS")
 for t in range(2):
-    for h in range(2):
-        w, b, n = (buf[(t * 2 + h) * 3 + i] for i in range(3))
-        if n:
-            print(f"  tile {t} half {h}: wait-for-S {w / n:7.1f} cyc  S->P {b / n:7.1f} cyc  period {(w + b) / n:7.1f}  ({n} tiles)")
+    w, b, n = (buf[t * 3 + i] for i in range(3))
+    if n:
+        print(f"  tile {t}: wait-for-S {w / n:7.1f} cyc  S->P {b / n:7.1f} cyc  period {(w + b) / n:7.1f}  ({n} sampled tiles)")
 c, ns, n = buf[20], buf[21], buf[22]
 if n:
-    print(f"  CTA lifetime: {c / n:.0f} cycles = {ns / n / 1e3:.1f} us -> SM clock {c / ns * 1e3:.0f} MHz; launches x CTAs = {n}; kernel {ms * 1e3:.1f} us")
-a, b, c2, n2 = buf[16], buf[17], buf[18], buf[19]
-if n2:
-    print(f"  per item (tile 0): wait first S {a / n2:.0f} cyc, tile loop {b / n2:.0f} cyc, epilogue {c2 / n2:.0f} cyc ({n2} items)")
-if buf[25]:
-    print(f"  pair-barrier wait: first tile {buf[24] / buf[25]:.0f} cyc, other tiles {buf[26] / max(1, buf[27]):.0f} cyc")
-if buf[25]:
-    print(f"  first tile: pass1 {buf[28] / buf[25]:.0f} cyc, whole softmax_tile {buf[29] / buf[25]:.0f} cyc; other tiles whole {buf[30] / max(1, buf[27]):.0f} cyc")
-if buf[14]:
-    n3 = buf[14]
-    print(f"  MMA warp per KV tile: wait V_j {buf[12] / n3:.0f} cyc, wait K_j+1 {buf[13] / n3:.0f} cyc, wait P halves (4 per tile) {buf[15] / n3:.0f} cyc total")
+    print(f"  CTA lifetime: {c / n:.0f} cycles = {ns / n / 1e3:.1f} us -> SM clock {c / ns * 1e3:.0f} MHz; kernel {ms * 1e3:.1f} us")
