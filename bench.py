@@ -122,6 +122,23 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def ncu_traffic(workload_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+    capture of this workload's kernel (profiles/), or None when no capture of it is committed."""
+    captures = {"cfg2_n8192_causal": "r01_v4_causal_n8192_summary.txt"}
+    f = captures.get(workload_name)
+    if not f:
+        return None
+    try:
+        tot = 0.0
+        for line in open(os.path.join(REPO, "profiles", f)):
+            if line.startswith("dram__bytes_read.sum [Mbyte]") or line.startswith("dram__bytes_write.sum [Mbyte]"):
+                tot += float(line.split("=")[1]) * 1e6
+        return tot or None
+    except OSError:
+        return None
+
+
 def cpu_baseline(workload, budget_rows=None):
     """The CPU oracle (port of cpu_attention, FA.cu:668-697) on a bounded, evenly spread row sample of
     the same workload, all host threads.  TFLOPS-equivalent = sampled rows' FLOPs / wall time."""
@@ -401,7 +418,7 @@ def main():
                         if args.impl == "ours" else "H2D x3 + flash_attention_v9_dispatch + D2H (FA.cu:774-780)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": round(tflops_rank, 2), "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": round(tflops_rank / pk["tflops"], 4), "traffic": None,
+                     "frac": round(tflops_rank / pk["tflops"], 4), "traffic": ncu_traffic(args.workload),
                      "peak_source": pk["source"] + ", cuBLAS bf16 burst",
                      "frac_of_sustained": round(tflops_rank / pk["tflops_sustained"], 4) if pk["tflops_sustained"] else None,
                      "frac_of_nominal_2250": round(tflops_rank / NOMINAL_FP16_TFLOPS, 4),
