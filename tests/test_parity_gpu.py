@@ -210,3 +210,80 @@ def test_host_buffer_entry_point(fa):
                                       out.ctypes.data_as(vp), 1, 2, 384, 128, 1)
     assert rc == 0
     gate(out, _oracle.attention(q, k, v, 1))
+
+
+# ---- memory safety without a sanitizer (compute-sanitizer is closed on this pool): canaries ----
+@pytest.mark.parametrize("N,D,causal", [(1, 128, 1), (127, 128, 0), (129, 64, 1), (300, 128, 1), (513, 64, 0)])
+def test_output_canaries_untouched(fa, N, D, causal):
+    B, H, pad = 2, 3, 4096
+    q, k, v = (torch.randn((B, H, N, D), device="cuda").half() for _ in range(3))
+    n = B * H * N * D
+    buf = torch.full((n + 2 * pad,), 1234.0, dtype=torch.float16, device="cuda")
+    out = buf[pad:pad + n].view(B, H, N, D)
+    assert out.data_ptr() % 16 == 0
+    fa.flash_attn_fwd(q, k, v, causal=bool(causal), out=out)
+    torch.cuda.synchronize()
+    assert bool((buf[:pad] == 1234.0).all()) and bool((buf[pad + n:] == 1234.0).all()), "write outside O"
+    assert not bool((out == 1234.0).all()), "O was not written"
+    assert not torch.isnan(out.float()).any()
+
+
+def test_two_streams_concurrently(fa):
+    # the dynamic scheduler uses one counter slot per launch: concurrent launches must not interfere
+    q, k, v = normal((1, 8, 1024, 128), seed=77)
+    ref = _oracle.attention(q, k, v, 1)
+    tq, tk, tv = (torch.from_numpy(x).cuda() for x in (q, k, v))
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    torch.cuda.synchronize()
+    for i in range(8):
+        with torch.cuda.stream(s1 if i % 2 == 0 else s2):
+            outs.append(fa.flash_attn_fwd(tq, tk, tv, causal=True))
+    torch.cuda.synchronize()
+    assert not fa.watchdog_status()["aborted"]
+    for o in outs:
+        gate(o.cpu().numpy(), ref, "concurrent streams")
+
+
+def test_many_back_to_back_launches_stay_deterministic(fa):
+    q, k, v = normal((1, 16, 768, 128), seed=78)
+    tq, tk, tv = (torch.from_numpy(x).cuda() for x in (q, k, v))
+    first = fa.flash_attn_fwd(tq, tk, tv, causal=True).clone()
+    out = torch.empty_like(first)
+    for _ in range(3000):                      # > 4096/2 scheduler slots, programmatic dependent launches
+        fa.flash_attn_fwd(tq, tk, tv, causal=True, out=out)
+    torch.cuda.synchronize()
+    assert not fa.watchdog_status()["aborted"]
+    assert torch.equal(first, out)
+
+
+def test_many_heads_short_sequences(fa):
+    q, k, v = normal((64, 40, 96, 64), seed=79)     # 2560 heads, one work item each
+    gate(gpu_attention(fa, q, k, v, 1), _oracle.attention(q, k, v, 1))
+
+
+# ---- BASELINE.json configs 3 and 5 at full size, row-sampled ----
+def _sampled_check(fa, B, H, N, D, causal, heads, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    tq, tk, tv = ((torch.rand((B, H, N, D), device="cuda", generator=g) - 0.5).half() for _ in range(3))
+    out = fa.flash_attn_fwd(tq, tk, tv, causal=bool(causal))
+    torch.cuda.synchronize()
+    assert not fa.watchdog_status()["aborted"]
+    rng = np.random.default_rng(seed)
+    rows = sample_rows(N, rng, n_random=8)
+    fq, fk, fv, fo = (t.view(B * H, N, D) for t in (tq, tk, tv, out))
+    for bh in heads:
+        q1, k1, v1 = (t[bh:bh + 1].unsqueeze(0).cpu().numpy() for t in (fq, fk, fv))
+        ref = _oracle.attention_rows(q1, k1, v1, causal, np.zeros(len(rows), np.int32), rows)
+        got = fo[bh][torch.from_numpy(rows.astype(np.int64)).cuda()].cpu().numpy()
+        gate(got, ref, f"B{B} H{H} N{N} head {bh}")
+    if causal:
+        assert torch.equal(out[:, :, 0, :], tv[:, :, 0, :])
+
+
+def test_config3_full_size_row_sampled(fa):
+    _sampled_check(fa, 16, 32, 8192, 128, 1, heads=[0, 255, 511], seed=3)
+
+
+def test_config5_full_size_row_sampled(fa):
+    _sampled_check(fa, 1, 32, 131072, 128, 1, heads=[0, 31], seed=5)
