@@ -54,7 +54,7 @@ class FlashAttnError(RuntimeError):
 class KernelInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "regs_per_thread", "local_bytes_per_thread", "static_smem_bytes", "dynamic_smem_bytes",
-        "threads_per_cta", "ctas", "tmem_columns", "kv_stages", "work_items", "num_sms")]
+        "threads_per_cta", "ctas", "tmem_columns", "kv_stages", "work_items", "num_sms", "cta_group")]
 
 
 def build(force: bool = False) -> str:
@@ -104,6 +104,9 @@ def lib() -> ctypes.CDLL:
     L.flash_attn_version.restype = ctypes.c_char_p
     L.flash_attn_debug_work_item.argtypes = [ci, ci, ci, ci, ci, ci, ci, ll] + [ctypes.POINTER(ci)] * 5
     L.flash_attn_debug_work_item.restype = ci
+    if hasattr(L, "flash_attn_debug_cta_group"):   # absent from archived A/B builds of older kernels
+        L.flash_attn_debug_cta_group.argtypes = [ci]
+        L.flash_attn_debug_cta_group.restype = ci
     L.flash_attn_debug_status.argtypes = [ctypes.POINTER(ctypes.c_uint)]
     L.flash_attn_debug_status.restype = ci
     _lib = L
@@ -192,4 +195,9 @@ def work_item(w: int, B: int, H: int, Nq: int, Nkv: int, D: int, causal: bool, s
                                           *[ctypes.byref(x) for x in vals])
     check(rc)
     total, bh, q0, n0, n1 = (x.value for x in vals)
-    return {"total": total, "bh": bh, "q0": q0, "n0": n0, "n1": n1}
+    return {"total": total, "bh": bh, "q0": q0, "n0": n0, "n1": n1, "n": max(n0, n1)}
+
+
+def cta_group(D: int) -> int:
+    """CTAs per work unit for this head_dim: a work item covers cta_group 128-row Q tiles."""
+    return int(lib().flash_attn_debug_cta_group(D))

@@ -8,6 +8,7 @@
 #include "../../include/flash_attn.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -52,10 +53,22 @@ void load_encode_fn() {
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
 }
 
-template <int D>
+template <int D, int CG>
 int set_kernel_attrs() {
-    return (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     fa::Cfg<D>::kSmemBytes);
+    return (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fa::Cfg<D, CG>::kSmemBytes);
+}
+
+// CTAs per work unit.  D = 128 runs as CTA pairs (tcgen05.mma.cta_group::2, M = 256); D = 64 keeps
+// one CTA per unit (its V half would be narrower than a 128-byte swizzle panel).  The environment
+// variable FLASH_ATTN_B200_CG=1 forces single CTAs for D = 128 as well (A/B measurements).
+int cta_group_for(int D) {
+    static const int forced = []() {
+        const char* e = getenv("FLASH_ATTN_B200_CG");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    if (D == 64 || forced == 1) return 1;
+    return 2;
 }
 
 // Per-device one-time setup.  Re-entrant from several host threads (one per GPU in the
@@ -73,8 +86,9 @@ DeviceState* device_state(int* err) {
         st->num_sms = prop.multiProcessorCount;
         st->cc_major = prop.major;
         if (prop.major != 10) { st->ok = FA_ERR_UNSUPPORTED_ARCH; return; }
-        int r = set_kernel_attrs<128>();
-        if (r == 0) r = set_kernel_attrs<64>();
+        int r = set_kernel_attrs<128, 1>();
+        if (r == 0) r = set_kernel_attrs<128, 2>();
+        if (r == 0) r = set_kernel_attrs<64, 1>();
         if (r == 0) r = (int)cudaMalloc(&st->sched, kSchedSlots * 2 * sizeof(int));
         if (r == 0) r = (int)cudaMemset(st->sched, 0, kSchedSlots * 2 * sizeof(int));
         st->ok = r;
@@ -83,13 +97,14 @@ DeviceState* device_state(int* err) {
     return st;
 }
 
-// [BH, N, D] fp16, box = 64 halves x 128 rows x 1 head, 128-byte swizzle; rows past N read as zero.
-int make_tmap(CUtensorMap* tm, const void* base, int BH, int N, int D) {
+// [BH, N, D] fp16, box = 64 halves x `rows` rows x 1 head, 128-byte swizzle; rows past N read as zero
+// and are dropped on store.
+int make_tmap(CUtensorMap* tm, const void* base, int BH, int N, int D, int rows = fa::kBlockN) {
     std::call_once(g_encode_once, load_encode_fn);
     if (!g_encode) return FA_ERR_TENSORMAP;
     cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)BH};
     cuuint64_t gstride[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)fa::kBlockN, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -114,8 +129,9 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     if (shift > 0x3fffffffLL) shift = 0x3fffffffLL;
     if (shift < -0x3fffffffLL) shift = -0x3fffffffLL;
     p.shift = (int)shift;
-    p.nqp = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
-    const long long tw = (long long)BH * p.nqp;
+    p.cg = cta_group_for(D);
+    p.nqu = (Nq + p.cg * fa::kBlockM - 1) / (p.cg * fa::kBlockM);
+    const long long tw = (long long)BH * p.nqu;
     p.total_work = (int)tw;
     // heads per scheduling group: K+V of the group <= 64 MB (half of B200's 126 MB L2)
     const long long kv_bytes = 2LL * Nkv * D * 2;
@@ -128,26 +144,30 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     return p;
 }
 
-template <int D>
+template <int D, int CG>
 int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-           fa::Params p, cudaStream_t stream) {
-    int grid = p.total_work < st->num_sms ? p.total_work : st->num_sms;
-    if (grid < 1) grid = 1;
+           const CUtensorMap& to, fa::Params p, cudaStream_t stream) {
+    int units = p.total_work < st->num_sms / CG ? p.total_work : st->num_sms / CG;
+    if (units < 1) units = 1;
     p.sched = st->sched + 2 * (st->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
     // launched with programmatic stream serialization (PDL): the kernel's prologue overlaps the tail
     // of its predecessor in the stream; it executes griddepcontrol.wait before touching global memory
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)grid);
+    cfg.gridDim = dim3((unsigned)(units * CG));
     cfg.blockDim = dim3(fa::kNumThreads);
-    cfg.dynamicSmemBytes = fa::Cfg<D>::kSmemBytes;
+    cfg.dynamicSmemBytes = fa::Cfg<D, CG>::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = CG;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D>, tq, tk, tv, p);
+    cfg.numAttrs = CG == 2 ? 2 : 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D, CG>, tq, tk, tv, to, p);
     if (le != cudaSuccess) return (int)le;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();   // FA.cu:662
@@ -157,13 +177,16 @@ int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaS
     int err = 0;
     DeviceState* st = device_state(&err);
     if (!st) return err;
-    if ((long long)p.BH * p.nqp > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
-    CUtensorMap tq, tk, tv;
+    if ((long long)p.BH * p.nqu > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
+    CUtensorMap tq, tk, tv, to;
     int rc;
     if ((rc = make_tmap(&tq, q, p.BH, p.Nq, D)) != FA_OK) return rc;
-    if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D)) != FA_OK) return rc;
+    if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D, fa::kBlockN / p.cg)) != FA_OK) return rc;
     if ((rc = make_tmap(&tv, v, p.BH, p.Nkv, D)) != FA_OK) return rc;
-    return D == 128 ? launch<128>(st, tq, tk, tv, p, stream) : launch<64>(st, tq, tk, tv, p, stream);
+    // O store map (unused in partial mode, where p.o aliases nothing: describe Q's extent on a valid pointer)
+    if ((rc = make_tmap(&to, p.o ? (const void*)p.o : q, p.BH, p.Nq, D)) != FA_OK) return rc;
+    if (D == 64) return launch<64, 1>(st, tq, tk, tv, to, p, stream);
+    return p.cg == 2 ? launch<128, 2>(st, tq, tk, tv, to, p, stream) : launch<128, 1>(st, tq, tk, tv, to, p, stream);
 }
 
 }  // namespace
@@ -249,8 +272,10 @@ int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_att
     if (B < 1 || H < 1 || N < 1) return FA_ERR_BAD_SHAPE;
     memset(info, 0, sizeof *info);
     cudaFuncAttributes attr;
-    cudaError_t e = D == 128 ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128>)
-                             : cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<64>);
+    const int cg = cta_group_for(D);
+    cudaError_t e = D == 64    ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<64, 1>)
+                    : cg == 2 ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, 2>)
+                              : cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, 1>);
     if (e != cudaSuccess) return (int)e;
     int err = 0;
     DeviceState* st = device_state(&err);
@@ -259,11 +284,19 @@ int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_att
     info->regs_per_thread = attr.numRegs;
     info->local_bytes_per_thread = (int)attr.localSizeBytes;
     info->static_smem_bytes = (int)attr.sharedSizeBytes;
-    info->dynamic_smem_bytes = D == 128 ? fa::Cfg<128>::kSmemBytes : fa::Cfg<64>::kSmemBytes;
+    info->dynamic_smem_bytes = D == 64    ? fa::Cfg<64, 1>::kSmemBytes
+                               : cg == 2 ? fa::Cfg<128, 2>::kSmemBytes
+                                         : fa::Cfg<128, 1>::kSmemBytes;
     info->threads_per_cta = fa::kNumThreads;
-    info->ctas = p.total_work < st->num_sms ? p.total_work : st->num_sms;
+    {
+        int units = p.total_work < st->num_sms / cg ? p.total_work : st->num_sms / cg;
+        info->ctas = (units < 1 ? 1 : units) * cg;
+    }
     info->tmem_columns = fa::kTmemCols;
-    info->kv_stages = D == 128 ? fa::Cfg<128>::kStages : fa::Cfg<64>::kStages;
+    info->kv_stages = D == 64    ? fa::Cfg<64, 1>::kKStages + fa::Cfg<64, 1>::kVStages
+                      : cg == 2 ? fa::Cfg<128, 2>::kKStages + fa::Cfg<128, 2>::kVStages
+                                : fa::Cfg<128, 1>::kKStages + fa::Cfg<128, 1>::kVStages;
+    info->cta_group = cg;
     info->work_items = p.total_work;
     info->num_sms = st->num_sms;
     return FA_OK;
@@ -303,7 +336,7 @@ const char* flash_attn_error_string(int code) {
     }
 }
 
-const char* flash_attn_version(void) { return "flashattn_b200 0.1 (sm_100a tcgen05/TMA forward)"; }
+const char* flash_attn_version(void) { return "flashattn_b200 0.2 (sm_100a tcgen05/TMA forward, CTA-pair MMA)"; }
 
 }  // extern "C"
 
@@ -318,13 +351,13 @@ extern "C" int flash_attn_debug_status(unsigned int* out4) {
 
 #ifdef FA_TIMING
 // debug builds only (-DFA_TIMING): in-kernel clock64 probes, see tests/harness/timing.py
-extern "C" int flash_attn_debug_timing(unsigned long long* out32, int reset) {
+extern "C" int flash_attn_debug_timing(unsigned long long* out32, int reset) {   // 64 counters
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemcpyFromSymbol(out32, fa::g_timing, 32 * sizeof(unsigned long long));
+    e = cudaMemcpyFromSymbol(out32, fa::g_timing, 64 * sizeof(unsigned long long));
     if (e != cudaSuccess) return (int)e;
     if (reset) {
-        unsigned long long z[32] = {0};
+        unsigned long long z[64] = {0};
         e = cudaMemcpyToSymbol(fa::g_timing, z, sizeof z);
     }
     return (int)e;
@@ -343,3 +376,5 @@ extern "C" int flash_attn_debug_work_item(int w, int B, int H, int Nq, int Nkv, 
     *bh = it.bh; *q0 = it.q0; *n0 = it.n0; *n1 = it.n1;
     return FA_OK;
 }
+// CTAs per work unit for this head_dim (1 or 2): how many 128-row Q tiles a work item covers
+extern "C" int flash_attn_debug_cta_group(int D) { return (D == 64 || D == 128) ? cta_group_for(D) : FA_ERR_BAD_HEAD_DIM; }

@@ -1,0 +1,718 @@
+// fa_fwd_sm100.cuh -- FlashAttention forward for B200 (sm_100a): persistent, warp-specialised,
+// TMA -> 128B-swizzled smem -> tcgen05.mma with S/P/O in tensor memory.
+//
+// Replaces the reference's device path flash_attention_v9<...> (flash_attention.cu:67-554):
+//   FA.cu:103-112  block->(bh, q-block) mapping, GRID_SWAP    -> persistent work loop, heavy-first
+//   FA.cu:145-159  Q fragments in registers                   -> Q tile pair resident in smem (TMA)
+//   FA.cu:417-447  synchronous K/V tile load + 2 barriers     -> producer warp, mbarrier ring
+//   FA.cu:188-233  DO_QK_MATMUL (mma.sync m16n8k16)           -> tcgen05.mma SS, S in TMEM
+//   FA.cu:235-288  DO_SOFTMAX (quad shuffles, eager rescale)  -> one thread per row, lazy rescale
+//   FA.cu:290-334  DO_PV_MATMUL (P in registers)              -> P fp16 in TMEM, tcgen05.mma TS
+//   FA.cu:497-553  epilogue via smem                          -> TMEM -> registers -> global
+//   FA.cu:460-496  split-K partial epilogue (dead code there) -> partial mode used by ring CP
+//
+// CTA = 384 threads:  warps 0-3  softmax/correction/epilogue for Q tile 0 (128 rows)
+//                     warps 4-7  same for Q tile 1
+//                     warp 8     TMEM allocator + tcgen05.mma issuer (one lane)
+//                     warp 9     TMA producer (one lane)
+//                     warps 10,11 idle (pad the third warpgroup)
+// One CTA per SM; each CTA loops over work items (bh, pair of 128-row Q tiles).
+//
+// TMEM (512 columns x 128 lanes x 32 bit): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).
+// P_t (fp16, two per column) overwrites columns [0,64) of S_t once the owning thread has read
+// its S row, and is handed to the MMA warp in two halves (keys 0-63, 64-127) so that the first four
+// PV k-steps run while the second half of the exponentials is still being computed.
+// Tensor-pipe order per KV tile j:  PV0(j) QK0(j+1) PV1(j) QK1(j+1), so each softmax warpgroup works
+// on S_t(j+1) while the tensor core runs the other tile's two MMAs.
+//
+// Why not 64-wide KV sub-tiles with S double-buffered (tried, profiles/r01_v3_subtile_*): QK^T with
+// N=64 in SS mode re-reads the Q slice from shared memory for half the math (192 B/clk > the 128 B/clk
+// smem port).  N=128 sits exactly at the port limit, so the S->P->PV->QK chain is shortened instead.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "sm100_ptx.cuh"
+
+namespace fa {
+
+using namespace sm100;
+
+constexpr int kBlockM = 128;      // Q rows per tile  (UMMA M)
+constexpr int kBlockN = 128;      // K/V rows per tile (UMMA N of QK^T, K extent of PV)
+constexpr int kNumThreads = 384;
+constexpr int kMmaWarp = 8;
+constexpr int kLoadWarp = 9;
+constexpr int kTmemCols = 512;
+constexpr int kRegsSoftmax = 208;   // setmaxnreg: softmax warpgroups grow, the producer/MMA warpgroup shrinks
+constexpr int kRegsOther = 80;      // 2*128*208 + 128*80 = 63488 <= 168 (launch) * 384
+constexpr float kRescaleThreshold = 8.0f;
+// Of every 4 element pairs, this many take exp2 on the FMA pipe (Cody-Waite + degree-3 minimax)
+// instead of MUFU.EX2: at 16 MUFU/clk/SM the 16384 exponentials of a 128x128 tile cost as many
+// cycles as its two MMAs, so the SFU -- not the tensor core -- would set the pace.
+#ifndef FA_POLY_PAIRS
+#define FA_POLY_PAIRS 1
+#endif
+constexpr int kPolyPairs = FA_POLY_PAIRS;  // lazy rescale: tolerate P up to 2^8 before moving the reference max
+
+template <int D>
+struct Cfg {
+    static_assert(D == 64 || D == 128, "head_dim must be 64 or 128");
+    static constexpr int kPanels = D / 64;                 // 128-byte swizzle panels per row
+    static constexpr int kPanelBytes = 128 * 128;          // 128 rows x 128 B
+    static constexpr int kTileBytes = kPanels * kPanelBytes;
+    static constexpr int kStages = (D == 128) ? 5 : 8;     // K/V ring entries (one tile each)
+    static constexpr int kSmemQ = 2 * kTileBytes;
+    static constexpr int kSmemKV = kStages * kTileBytes;
+    static constexpr int kBarOffset = kSmemQ + kSmemKV;
+    static constexpr int kNumBars = 2 + 2 * kStages + 8 + 4;
+    static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 32 + 1024;  // +32: tmem slot, scheduler slots; +1024: manual alignment slack
+    static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
+    static constexpr uint32_t kIdescQK = umma_idesc_f16(kBlockM, kBlockN, 0, 0);
+    static constexpr uint32_t kIdescPV = umma_idesc_f16(kBlockM, D, 0, 1);  // V is MN-major ([kv][d], d contiguous)
+};
+
+struct Params {
+    __half* o;          // fp16 output [BH, Nq, D]            (partial_mode == 0)
+    float* o_partial;   // fp32 un-normalised [BH*Nq, D]       (partial_mode == 1; FA.cu:460-496 format)
+    float* ml;          // (m, l) pairs [BH*Nq, 2]
+    int Nq, Nkv, BH;
+    int causal;
+    int shift;          // q_offset - kv_offset: key c visible to query r iff c <= r + shift
+    int nqp;            // Q tile pairs per head = ceil(Nq / 256)
+    int total_work;     // BH * nqp
+    int group_heads;    // heads per scheduling group (their K/V working set is sized to stay in L2)
+    int partial_mode;
+    int accumulate;
+    int* sched;         // {next work index, finished CTAs}: dynamic tile scheduler state, self-resetting
+    float scale;        // 1/sqrt(D)
+    float scale_log2;   // scale * log2(e)
+};
+
+// ---- work decomposition (shared by host tests and every warp role) ----
+struct WorkItem {
+    int bh, q0;      // head index, first local query row of the pair
+    int n0, n1;      // KV tiles the two Q tiles need (0 = nothing visible / tile absent)
+};
+__host__ __device__ inline int kv_trip_count(int q_start, int Nq, int Nkv, int causal, int shift) {
+    if (q_start >= Nq) return 0;
+    const int nkv_tiles = (Nkv + kBlockN - 1) / kBlockN;
+    if (!causal) return nkv_tiles;
+    int last_row = q_start + kBlockM - 1;
+    if (last_row > Nq - 1) last_row = Nq - 1;
+    long long vis = (long long)last_row + shift + 1;  // keys [0, vis) visible to the last row
+    if (vis <= 0) return 0;
+    if (vis > Nkv) vis = Nkv;
+    return (int)((vis + kBlockN - 1) / kBlockN);
+}
+// Work order (replaces GRID_SWAP / reversed q-blocks, FA.cu:103-112).  Heads are taken in groups whose
+// K/V fit comfortably in L2; inside a group the order is heaviest Q pair first ACROSS the group's
+// heads (causal: the last pair sees the most keys), so the dynamic scheduler hands out long items
+// early and the tail of the launch is made of the lightest ones, while the CTAs running at any moment
+// still share a few heads' K/V through L2.
+__host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
+    WorkItem it;
+    const int per_group = p.group_heads * p.nqp;
+    const int g = w / per_group;
+    const int r = w - g * per_group;
+    int heads = p.BH - g * p.group_heads;
+    if (heads > p.group_heads) heads = p.group_heads;
+    const int qp = p.nqp - 1 - r / heads;
+    it.bh = g * p.group_heads + r % heads;
+    it.q0 = qp * 2 * kBlockM;
+    it.n0 = kv_trip_count(it.q0, p.Nq, p.Nkv, p.causal, p.shift);
+    it.n1 = kv_trip_count(it.q0 + kBlockM, p.Nq, p.Nkv, p.causal, p.shift);
+    return it;
+}
+
+#ifdef FA_TIMING
+__device__ unsigned long long g_timing[32];
+#endif
+
+struct Ring {
+    uint32_t idx, phase;
+    template <int kStages>
+    __device__ __forceinline__ void advance() {
+        if (++idx == (uint32_t)kStages) { idx = 0; phase ^= 1u; }
+    }
+};
+
+// ---- exp2 of a pair of (already scaled and shifted) scores ----
+// kPoly = false: two MUFU.EX2.  kPoly = true: FMA/ALU pipes only.  x = n + f, n = round(x),
+// f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, below the
+// 4.9e-4 of the fp16 rounding P gets anyway); 2^n by adding n into the exponent field.
+template <bool kPoly>
+__device__ __forceinline__ void exp2_pair(uint64_t x2, float& p0, float& p1) {
+    if (!kPoly) {
+        float x0, x1;
+        unpack_f32x2(x2, x0, x1);
+        p0 = ex2_approx(x0);
+        p1 = ex2_approx(x1);
+    } else {
+        float x0, x1;
+        unpack_f32x2(x2, x0, x1);
+        x0 = fmaxf(x0, -126.0f);                       // masked (-inf) and far-away scores -> 2^-126 ~ 0
+        x1 = fmaxf(x1, -126.0f);
+        x2 = pack_f32x2(x0, x1);
+        const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);        // 1.5 * 2^23: rounds to integer
+        const uint64_t t2 = add_f32x2(x2, magic);
+        const uint64_t n2 = add_f32x2(t2, pack_f32x2(-12582912.0f, -12582912.0f));
+        const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.0f, -1.0f), x2);
+        uint64_t q2 = fma_f32x2(pack_f32x2(0.05517143756151199f, 0.05517143756151199f), f2,
+                                pack_f32x2(0.24261081218719482f, 0.24261081218719482f));
+        q2 = fma_f32x2(q2, f2, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+        q2 = fma_f32x2(q2, f2, pack_f32x2(0.9999281167984009f, 0.9999281167984009f));
+        float t0, t1, q0, q1;
+        unpack_f32x2(t2, t0, t1);
+        unpack_f32x2(q2, q0, q1);
+        p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+        p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+    }
+}
+
+// exponentials + fp16 packing of 64 consecutive columns (one half of the tile)
+__device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64_t scale2, uint64_t neg2,
+                                         uint64_t& sum_a, uint64_t& sum_b) {
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int e = i + 2 * q;
+            const uint64_t x2 =
+                fma_f32x2(pack_f32x2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, neg2);
+            float p0, p1;
+#ifdef FA_SKELETON
+            unpack_f32x2(x2, p0, p1);
+#else
+            if (q < kPolyPairs) exp2_pair<true>(x2, p0, p1);
+            else exp2_pair<false>(x2, p0, p1);
+#endif
+            if (q & 1) sum_b = add_f32x2(sum_b, pack_f32x2(p0, p1));   // row sum of the un-rounded p (FA.cu:273-279)
+            else sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
+            __half2 h = __floats2half2_rn(p0, p1);                     // low half = even column
+            pk[e / 2] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+}
+
+// ---- softmax of one 128x128 S tile; one thread owns one row ----
+template <int D, bool kMask>
+__device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
+                                             uint32_t bar_o_full, int lim_local, bool have_o,
+                                             uint32_t pv_count, float& m_ref, float& l_run) {
+    uint32_t s[kBlockN];
+    tmem_ld_x32(tS + 0, s + 0);
+    tmem_ld_x32(tS + 32, s + 32);
+    tmem_ld_x32(tS + 64, s + 64);
+    tmem_ld_x32(tS + 96, s + 96);
+    tmem_wait_ld();
+
+    if (kMask) {
+#pragma unroll
+        for (int i = 0; i < kBlockN; i++)
+            if (i >= lim_local) s[i] = 0xff800000u;  // -inf
+    }
+
+    // row max: 3-input max (FMNMX3), four independent chains
+    float mx0 = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1]));
+    float mx1 = fmaxf(__uint_as_float(s[2]), __uint_as_float(s[3]));
+    float mx2 = fmaxf(__uint_as_float(s[4]), __uint_as_float(s[5]));
+    float mx3 = fmaxf(__uint_as_float(s[6]), __uint_as_float(s[7]));
+#pragma unroll
+    for (int i = 8; i < kBlockN; i += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+    }
+    const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    const float m_new = fmaxf(m_ref, m_tile);
+
+    // Lazy rescale (replaces the reference's every-tile O *= alpha, FA.cu:267-270): the reference
+    // max only moves when the true max has outgrown it by 2^kRescaleThreshold.
+    const bool need = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;  // NaN (-inf - -inf) -> false
+    if (__any_sync(0xffffffffu, need)) {
+        if (have_o) {
+            const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
+            const uint64_t alpha2 = pack_f32x2(alpha, alpha);
+            // O_t holds PV(0..j-1); the last of them must have retired before we touch it
+            mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 40);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < D; c += 32) {
+                uint32_t o[32];
+                tmem_ld_x32(tO + c, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float lo, hi;
+                    unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), lo, hi);
+                    o[i] = __float_as_uint(lo);
+                    o[i + 1] = __float_as_uint(hi);
+                }
+                tmem_st_x32(tO + c, o);
+            }
+            l_run *= alpha;
+        }
+        m_ref = m_new;
+    }
+
+    const float m_used = (m_ref == -INFINITY) ? 0.0f : m_ref;
+    const float neg = -m_used * p.scale_log2;
+    const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+    const uint64_t neg2 = pack_f32x2(neg, neg);
+    uint64_t sum_a = 0ull, sum_b = 0ull;     // (0.f, 0.f)
+    uint32_t pk[32];
+    // P_t (fp16 A operand of PV) overwrites columns [0,64) of S_t, delivered in two halves:
+    // keys 0-63 -> columns [0,32) -> barrier half 0, keys 64-127 -> columns [32,64) -> half 1
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        exp_half(s + 64 * h, pk, scale2, neg2, sum_a, sum_b);
+        tmem_st_x32(tS + 32 * h, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(bar_p_full + 8 * h);   // one arrival per warp (barrier count 4)
+    }
+    float a0, a1;
+    unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
+    l_run += a0 + a1;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kNumThreads, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, const Params p) {
+    using C = Cfg<D>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = smem_base;
+    const uint32_t sKV = smem_base + C::kSmemQ;
+    const uint32_t bars = smem_base + C::kBarOffset;
+    const uint32_t bar_q_full = bars + 0;
+    const uint32_t bar_q_empty = bars + 8;
+    const uint32_t bar_kv_full = bars + 16;                       // [kStages]
+    const uint32_t bar_kv_empty = bar_kv_full + 8 * C::kStages;   // [kStages]
+    const uint32_t bar_s_full = bar_kv_empty + 8 * C::kStages;    // [tile]
+    const uint32_t bar_p_full = bar_s_full + 16;                  // [tile][half]  index 2*t + h
+    const uint32_t bar_o_full = bar_p_full + 32;                  // [tile]
+    const uint32_t bar_sched_full = bar_o_full + 16;              // [2] work-index slots, producer -> everyone
+    const uint32_t bar_sched_empty = bar_sched_full + 16;         // [2]
+    const uint32_t tmem_slot = bar_sched_empty + 16;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    volatile int* sched_w = reinterpret_cast<volatile int*>(tmem_slot_ptr + 2);   // [2]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+#ifdef FA_TIMING
+    long long k_c0 = 0;
+    unsigned long long k_t0 = 0;
+    if (threadIdx.x == 0) {
+        k_c0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_t0));
+    }
+#endif
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_q_full, 1);
+        mbar_init(bar_q_empty, 1);
+        for (int i = 0; i < C::kStages; i++) {
+            mbar_init(bar_kv_full + 8 * i, 1);
+            mbar_init(bar_kv_empty + 8 * i, 1);
+        }
+        for (int t = 0; t < 2; t++) {
+            mbar_init(bar_s_full + 8 * t, 1);
+            mbar_init(bar_p_full + 16 * t, 4);        // one arrival per softmax warp of the tile,
+            mbar_init(bar_p_full + 16 * t + 8, 4);    // per half of P
+            mbar_init(bar_o_full + 8 * t, 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(bar_sched_full + 8 * i, 1);
+            mbar_init(bar_sched_empty + 8 * i, 9);    // MMA warp + 8 softmax warps
+        }
+        fence_mbar_init();
+    }
+    if (warp == kMmaWarp) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    if (warp == kLoadWarp && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+    // prefetch) may overlap the tail of the previous kernel in the stream; global memory is only
+    // touched below this point.  The next kernel's prologue may start as soon as our CTAs retire.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    // Dynamic tile scheduler (replaces the reference's static blockIdx mapping, FA.cu:103-112): the
+    // producer warp claims work indices (first one static, the rest from a global counter) and
+    // publishes them through a 2-slot smem mailbox; every consumer warp reads slot i&1 for its i-th
+    // item.  Work order is heads-outermost, heaviest Q pair first (decode_work), so the causal tail is
+    // made of the lightest items.  Returns -1 when the grid has run out of work.
+    auto next_work = [&](uint32_t i) -> int {
+        const uint32_t slot = i & 1u;
+        mbar_wait(bar_sched_full + 8 * slot, (i >> 1) & 1u, 50);
+        const int w = sched_w[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sched_empty + 8 * slot);
+        return w;
+    };
+
+    // The producer and MMA warps run their loops converged (all 32 lanes take the same branches
+    // and waits); the instructions with side effects sit under elect_one().  Warp-uniform control
+    // flow keeps descriptors and barrier addresses in uniform registers -- in a lane-divergent
+    // region every UTCHMMA costs an extra ELECT / R2UR.BROADCAST sequence and the single issuing
+    // thread becomes the bottleneck of the whole CTA (profiles/r01_v1_full_n8192_summary.txt).
+    if (warp >= 8) {
+    setmaxnreg_dec<kRegsOther>();   // each role's code must be dominated by its own setmaxnreg
+    if (warp == kLoadWarp) {
+        // =============================== TMA producer ===============================
+        Ring ring{0u, 0u};
+        for (uint32_t it = 0;; ++it) {
+            // claim the next work item and publish it
+            const uint32_t slot = it & 1u;
+            mbar_wait(bar_sched_empty + 8 * slot, ((it >> 1) & 1u) ^ 1u, 3);
+            int w = 0;
+            if (lane == 0) w = (it == 0) ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(p.sched, 1);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w >= p.total_work) w = -1;
+            if (lane == 0) {
+                sched_w[slot] = w;
+                mbar_arrive(bar_sched_full + 8 * slot);   // release: the slot write is visible to waiters
+            }
+            __syncwarp();
+            if (w < 0) break;
+            const WorkItem wi = decode_work(w, p);
+            const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
+            const bool have_q1 = wi.q0 + kBlockM < p.Nq;
+            mbar_wait(bar_q_empty, (it & 1u) ^ 1u, 1);   // previous item's QK^T MMAs retired
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_q_full, (have_q1 ? 2 : 1) * C::kTileBytes);
+                for (int t = 0; t < (have_q1 ? 2 : 1); t++)
+                    for (int pn = 0; pn < C::kPanels; pn++)
+                        tma_load_3d(sQ + t * C::kTileBytes + pn * C::kPanelBytes, &tmQ, bar_q_full, pn * 64,
+                                    wi.q0 + t * kBlockM, wi.bh);
+            }
+            __syncwarp();
+            for (int j = 0; j < nmax; j++) {
+                // ring order K_0 V_0 K_1 V_1 ... (the order the MMA warp releases them in)
+#pragma unroll
+                for (int kv = 0; kv < 2; kv++) {
+                    const uint32_t full = bar_kv_full + 8 * ring.idx;
+                    mbar_wait(bar_kv_empty + 8 * ring.idx, ring.phase ^ 1u, 2);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(full, C::kTileBytes);
+                        const uint32_t dst = sKV + ring.idx * C::kTileBytes;
+#pragma unroll
+                        for (int pn = 0; pn < C::kPanels; pn++)
+                            tma_load_3d(dst + pn * C::kPanelBytes, kv == 0 ? &tmK : &tmV, full, pn * 64,
+                                        j * kBlockN, wi.bh);
+                    }
+                    __syncwarp();
+                    ring.advance<C::kStages>();
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // =============================== tcgen05.mma issuer ===============================
+        Ring rk{0u, 0u};              // ring entry holding K_j
+        Ring rv{1u % C::kStages, 0u}; // ring entry holding V_j
+        uint32_t it = 0;
+        uint32_t p_phase0 = 0u, p_phase1 = 0u;
+        const uint32_t tS0 = tmem_base + C::kTmemS0, tS1 = tmem_base + C::kTmemS1;
+        const uint32_t tO0 = tmem_base + C::kTmemO0, tO1 = tmem_base + C::kTmemO1;
+        const uint64_t qdesc0 = umma_smem_desc(sQ, 16, 1024);
+        const uint64_t qdesc1 = umma_smem_desc(sQ + C::kTileBytes, 16, 1024);
+
+        // S_t = Q_t K_j^T : D/16 k-steps; k-step ks lives in panel ks/4 at byte offset (ks%4)*32
+        auto issue_qk = [&](uint32_t tS, uint64_t qdesc, uint32_t k_smem, uint32_t bar) {
+            const uint64_t kdesc = umma_smem_desc(k_smem, 16, 1024);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ks++) {
+                    const uint64_t off = (uint64_t)(((ks >> 2) * C::kPanelBytes + (ks & 3) * 32) >> 4);
+                    umma_ss(tS, qdesc + off, kdesc + off, C::kIdescQK, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(bar);
+            }
+            __syncwarp();
+        };
+        // O_t (+)= P_t V_j : 8 k-steps of 16 kv rows (P k-step = 8 TMEM columns, V k-step = 16 rows * 128 B),
+        // issued in two halves of 4 k-steps as the two halves of P arrive
+        auto issue_pv = [&](uint32_t tO, uint32_t tP, uint32_t v_smem, bool accumulate, uint32_t bar_p,
+                            uint32_t parity, uint32_t bar_o, int tag) {
+            const uint64_t vdesc = umma_smem_desc(v_smem, C::kPanelBytes, 1024);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                mbar_wait(bar_p + 8 * h, parity, tag);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 4 * h; ks < 4 * h + 4; ks++)
+                        umma_ts(tO, tP + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV,
+                                (accumulate || ks > 0) ? 1u : 0u);
+                    if (h == 1) umma_commit(bar_o);
+                }
+                __syncwarp();
+            }
+        };
+        auto commit = [&](uint32_t bar) {
+            if (elect_one()) umma_commit(bar);
+            __syncwarp();
+        };
+
+        for (;; ++it) {
+            const int w = next_work(it);
+            if (w < 0) break;
+            const WorkItem wi = decode_work(w, p);
+            const int n0 = wi.n0, n1 = wi.n1;
+            const int nmax = n0 > n1 ? n0 : n1;
+            mbar_wait(bar_q_full, it & 1u, 10);
+            tc_fence_after();
+            if (nmax > 0) {
+                mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 11);
+                tc_fence_after();
+                const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
+                if (n0 > 0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
+                if (n1 > 0) issue_qk(tS1, qdesc1, k_smem, bar_s_full + 8);
+                commit(bar_kv_empty + 8 * rk.idx);
+                rk.advance<C::kStages>(); rk.advance<C::kStages>();
+            }
+            // Q is free for the next item as soon as the last QK^T of this one has retired
+            if (nmax <= 1) commit(bar_q_empty);
+            for (int j = 0; j < nmax; j++) {
+                const bool has_next = j + 1 < nmax;
+                mbar_wait(bar_kv_full + 8 * rv.idx, rv.phase, 12);
+                const uint32_t v_smem = sKV + rv.idx * C::kTileBytes;
+                const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
+                // ---- tile 0: PV0(j), QK0(j+1)
+                if (j < n0) {
+                    issue_pv(tO0, tS0, v_smem, j > 0, bar_p_full, p_phase0, bar_o_full, 13);
+                    p_phase0 ^= 1u;
+                }
+                if (has_next) {
+                    mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 15);
+                    tc_fence_after();
+                }
+                if (j + 1 < n0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
+                // ---- tile 1: PV1(j), QK1(j+1)
+                if (j < n1) {
+                    issue_pv(tO1, tS1, v_smem, j > 0, bar_p_full + 16, p_phase1, bar_o_full + 8, 14);
+                    p_phase1 ^= 1u;
+                }
+                commit(bar_kv_empty + 8 * rv.idx);
+                rv.advance<C::kStages>(); rv.advance<C::kStages>();
+                if (j + 1 < n1) issue_qk(tS1, qdesc1, k_smem, bar_s_full + 8);
+                if (has_next) {
+                    commit(bar_kv_empty + 8 * rk.idx);
+                    rk.advance<C::kStages>(); rk.advance<C::kStages>();
+                    if (j + 2 == nmax) commit(bar_q_empty);   // QK^T(nmax-1) was the last reader of Q
+                }
+            }
+        }
+    }
+    } else {
+        setmaxnreg_inc<kRegsSoftmax>();
+        // =============================== softmax / correction / epilogue ===============================
+        const int t = warp >> 2;                               // which Q tile of the pair
+        const int row_in_tile = (warp & 3) * 32 + lane;        // TMEM lane == S/O row
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem_base + lane_base + (t ? C::kTmemS1 : C::kTmemS0);
+        const uint32_t tO = tmem_base + lane_base + (t ? C::kTmemO1 : C::kTmemO0);
+        const uint32_t my_s_full = bar_s_full + 8 * t;
+        const uint32_t my_p_full = bar_p_full + 16 * t;        // + 8 * half
+        const uint32_t my_o_full = bar_o_full + 8 * t;
+        uint32_t s_phase = 0;
+        uint32_t pv_count = 0;   // P tiles handed to the MMA warp so far == o_full completions expected
+
+        for (uint32_t it = 0;; ++it) {
+            const int w = next_work(it);
+            if (w < 0) break;
+            const WorkItem wi = decode_work(w, p);
+            const int q_start = wi.q0 + t * kBlockM;
+            if (q_start >= p.Nq) continue;                     // this Q tile does not exist
+            const int n_t = t ? wi.n1 : wi.n0;
+            const int row = q_start + row_in_tile;             // local query row
+            // keys [0, lim) are visible to this row
+            long long lim_ll = p.causal ? (long long)row + p.shift + 1 : (long long)p.Nkv;
+            if (lim_ll > p.Nkv) lim_ll = p.Nkv;
+            if (lim_ll < 0) lim_ll = 0;
+            const int lim = (int)lim_ll;
+
+            float m_ref = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < n_t; j++) {
+#ifdef FA_TIMING
+                const long long tw0 = clock64();
+#endif
+                mbar_wait(my_s_full, s_phase, 20 + t);
+                s_phase ^= 1u;
+                tc_fence_after();
+#ifdef FA_TIMING
+                const long long tw1 = clock64();
+#endif
+                const int k0 = j * kBlockN;
+                const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
+                if (need_mask)
+                    softmax_tile<D, true>(p, tS, tO, my_p_full, my_o_full, lim - k0, j > 0, pv_count, m_ref, l_run);
+                else
+                    softmax_tile<D, false>(p, tS, tO, my_p_full, my_o_full, kBlockN, j > 0, pv_count, m_ref, l_run);
+                ++pv_count;
+#ifdef FA_TIMING
+                if (lane == 0 && (warp & 3) == 0 && j > 0 && (j & 7) == 0) {   // sampled: 1 tile in 8
+                    const long long tw2 = clock64();
+                    atomicAdd(&g_timing[t * 3 + 0], (unsigned long long)(tw1 - tw0));
+                    atomicAdd(&g_timing[t * 3 + 1], (unsigned long long)(tw2 - tw1));
+                    atomicAdd(&g_timing[t * 3 + 2], 1ull);
+                }
+#endif
+            }
+
+            // ---- epilogue: O_t / l -> fp16 -> global (or the partial-state format) ----
+            if (n_t > 0) {
+                mbar_wait(my_o_full, (pv_count - 1u) & 1u, 30 + t);
+                tc_fence_after();
+            }
+            const bool row_ok = row < p.Nq;
+            const size_t grow = (size_t)wi.bh * p.Nq + row;
+            if (!p.partial_mode) {
+                const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;   // FA.cu:502-503
+                __half* orow = p.o + grow * D;
+#pragma unroll
+                for (int c = 0; c < D; c += 32) {
+                    uint32_t o[32];
+                    if (n_t > 0) {
+                        tmem_ld_x32(tO + c, o);
+                        tmem_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) o[i] = 0u;
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 v;
+                            __half2 h;
+                            h = __floats2half2_rn(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
+                            v.x = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2half2_rn(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                            v.y = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2half2_rn(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                            v.z = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2half2_rn(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+                            v.w = *reinterpret_cast<uint32_t*>(&h);
+                            *reinterpret_cast<uint4*>(orow + c + i) = v;
+                        }
+                    }
+                }
+            } else {
+                // partial state (FA.cu:460-496): un-normalised fp32 O, (m, l) with m in the
+                // scaled-score (natural-log) domain; merge algebra of FA.cu:575-597 when accumulating
+                float m_out = (m_ref == -INFINITY) ? -FLT_MAX : m_ref * p.scale;
+                float l_out = l_run;
+                float w_new = 1.f, w_old = 0.f;
+                float* prow = p.o_partial + grow * D;
+                if (p.accumulate && row_ok) {
+                    const float m_old = p.ml[grow * 2 + 0];
+                    const float l_old = p.ml[grow * 2 + 1];
+                    const float m_max = fmaxf(m_old, m_out);
+                    const float kLog2e = 1.4426950408889634f;
+                    w_old = (m_old <= -FLT_MAX) ? 0.f : ex2_approx((m_old - m_max) * kLog2e);
+                    w_new = (m_out <= -FLT_MAX) ? 0.f : ex2_approx((m_out - m_max) * kLog2e);
+                    l_out = l_old * w_old + l_run * w_new;
+                    m_out = m_max;
+                }
+#pragma unroll
+                for (int c = 0; c < D; c += 32) {
+                    uint32_t o[32];
+                    if (n_t > 0) {
+                        tmem_ld_x32(tO + c, o);
+                        tmem_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) o[i] = 0u;
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 v = make_float4(__uint_as_float(o[i]) * w_new, __uint_as_float(o[i + 1]) * w_new,
+                                                   __uint_as_float(o[i + 2]) * w_new, __uint_as_float(o[i + 3]) * w_new);
+                            if (p.accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(prow + c + i);
+                                v.x += old.x * w_old; v.y += old.y * w_old;
+                                v.z += old.z * w_old; v.w += old.w * w_old;
+                            }
+                            *reinterpret_cast<float4*>(prow + c + i) = v;
+                        }
+                    }
+                }
+                if (row_ok) {
+                    p.ml[grow * 2 + 0] = m_out;
+                    p.ml[grow * 2 + 1] = l_out;
+                }
+            }
+            // O_t / S_t are free again: the next item's first P arrival orders after these reads
+            tc_fence_before();
+        }
+    }
+
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+#ifdef FA_TIMING
+    if (threadIdx.x == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        atomicAdd(&g_timing[20], (unsigned long long)(clock64() - k_c0));   // CTA lifetime, SM cycles
+        atomicAdd(&g_timing[21], t1 - k_t0);                                // CTA lifetime, ns
+        atomicAdd(&g_timing[22], 1ull);
+    }
+#endif
+    if (threadIdx.x == 0) {
+        // last CTA out re-arms the scheduler state for the launch that reuses this slot
+        __threadfence();
+        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
+        }
+    }
+    if (warp == kMmaWarp) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// fp16 O = o_partial / l  (final step of the FA.cu:575-597 merge)
+__global__ void fa_finalize_kernel(const float* __restrict__ o_partial, const float* __restrict__ ml,
+                                   __half* __restrict__ o, long long rows, int D) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
+    const int per_row = D / 4;
+    const long long r = idx / per_row;
+    if (r >= rows) return;
+    const int c = (int)(idx % per_row) * 4;
+    const float l = ml[r * 2 + 1];
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    const float4 v = *reinterpret_cast<const float4*>(o_partial + r * D + c);
+    __half2 a = __floats2half2_rn(v.x * inv, v.y * inv);
+    __half2 b = __floats2half2_rn(v.z * inv, v.w * inv);
+    uint2 out;
+    out.x = *reinterpret_cast<uint32_t*>(&a);
+    out.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(o + r * D + c) = out;
+}
+
+}  // namespace fa

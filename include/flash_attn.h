@@ -71,9 +71,10 @@ typedef struct {
     int threads_per_cta;
     int ctas; /* persistent grid size */
     int tmem_columns;
-    int kv_stages;
-    int work_items; /* (b,h,q-tile-pair) units the grid loops over */
+    int kv_stages; /* K ring entries + V ring entries */
+    int work_items; /* (b, h, q-unit) units the grid loops over; a unit is cta_group Q tiles of 128 rows */
     int num_sms;
+    int cta_group; /* CTAs cooperating on one unit: 2 = tcgen05.mma.cta_group::2 pairs (D = 128), 1 otherwise */
 } flash_attn_kernel_info;
 int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_attn_kernel_info* info);
 

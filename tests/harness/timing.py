@@ -13,7 +13,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 causal = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
 L = fa.lib()
 L.flash_attn_debug_timing.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
-buf = (ctypes.c_ulonglong * 32)()
+buf = (ctypes.c_ulonglong * 64)()
 g = torch.Generator(device="cuda").manual_seed(0)
 q, k, v = ((torch.rand((1, 32, N, 128), device="cuda", generator=g) - 0.5).half() for _ in range(3))
 o = torch.empty_like(q)
@@ -37,3 +37,15 @@ for t in range(2):
 c, ns, n = buf[20], buf[21], buf[22]
 if n:
     print(f"  CTA lifetime: {c / n:.0f} cycles = {ns / n / 1e3:.1f} us -> SM clock {c / ns * 1e3:.0f} MHz; kernel {ms * 1e3:.1f} us")
+
+nt = max(1, buf[2])   # sampled tiles of set 0 ~ probe samples are 1 in 8 of warp 0's tiles
+names = ["ld S + s_free", "mask+max", "wait m_ready", "decide+publish", "exp h0", "wait pv_done", "st+arrive h0",
+         "exp h1", "(pv wait h1)", "st+arrive h1"]
+tot = sum(buf[32 + i] for i in range(10))
+if tot:
+    print("  softmax phases (share of S->P, warp 0): " + ", ".join(f"{n} {100.0 * buf[32 + i] / tot:.1f}%" for i, n in enumerate(names)))
+mn = ["QK: wait K", "QK: wait s_free", "QK: issue+commit", "PV: wait V", "PV: wait o_free", "PV: wait P h0", "PV: issue h0",
+      "PV: wait P h1", "PV: issue h1", "PV: commit"]
+npv = buf[48 + 10]
+if npv:
+    print("  MMA warp cycles per PV tile (all CTAs): " + ", ".join(f"{n} {buf[48 + i] / npv:.0f}" for i, n in enumerate(mn)))

@@ -1,4 +1,4 @@
-"""CPU-only: the persistent kernel's work decomposition (host mirror of fa::decode_work, which
+"""CPU-only: the persistent kernel's work decomposition (a work item = one head x cta_group 128-row Q tiles) (host mirror of fa::decode_work, which
 replaces the reference's blockIdx mapping / GRID_SWAP, flash_attention.cu:103-112): every
 (head, q-tile) exactly once, heavy-first inside a head, fully masked KV tiles skipped."""
 import pytest
@@ -22,9 +22,12 @@ def test_every_q_tile_exactly_once(N, causal):
     B, H = 2, 3
     its = items(B, H, N, N, 128, causal)
     nq_tiles = (N + 127) // 128
+    cg = fa.cta_group(128)
     seen = set()
     for it in its:
-        for t in range(2):
+        if cg == 1:
+            assert it["n1"] == 0
+        for t in range(cg):
             q_start = it["q0"] + 128 * t
             n = it["n1"] if t else it["n0"]
             if q_start < N:
@@ -41,21 +44,21 @@ def test_every_q_tile_exactly_once(N, causal):
 def test_heavy_first_within_l2_sized_head_groups():
     # N=8192 D=128: K+V of a head = 4 MB -> 16 heads per group; inside a group heavy-first across heads
     its = items(1, 32, 8192, 8192, 128, True)
-    nqp = 32
+    nqp = 64 // fa.cta_group(128)
     per_group = 16 * nqp
     assert len(its) == 32 * nqp
     for g in range(2):
         grp = its[g * per_group:(g + 1) * per_group]
         assert {it["bh"] for it in grp} == set(range(16 * g, 16 * g + 16))
-        w = [it["n0"] + it["n1"] for it in grp]
+        w = [it["n"] for it in grp]
         assert w == sorted(w, reverse=True)
     # the launch ends with the lightest items
-    assert its[-1]["n0"] + its[-1]["n1"] == min(it["n0"] + it["n1"] for it in its)
+    assert its[-1]["n"] == min(it["n"] for it in its)
 
 
 def test_short_sequences_form_one_group():
     its = items(1, 4, 2048, 2048, 128, True)
-    w = [it["n0"] + it["n1"] for it in its]
+    w = [it["n"] for it in its]
     assert w == sorted(w, reverse=True)          # pure heavy-first: all heads fit one group
     assert [it["bh"] for it in its[:4]] == [0, 1, 2, 3]
 
@@ -64,8 +67,9 @@ def test_last_group_may_be_smaller():
     # 5 heads of 16 MB K/V each (N=32768): groups of 4 + 1, every (head, pair) still exactly once
     its = items(1, 5, 32768, 32768, 128, True)
     seen = {(it["bh"], it["q0"]) for it in its}
-    assert len(seen) == len(its) == 5 * 128
-    assert [it["bh"] for it in its[:4]] == [0, 1, 2, 3] and its[4 * 128]["bh"] == 4
+    units = 256 // fa.cta_group(128)
+    assert len(seen) == len(its) == 5 * units
+    assert [it["bh"] for it in its[:4]] == [0, 1, 2, 3] and its[4 * units]["bh"] == 4
 
 
 def test_masked_tiles_skipped_with_offsets():
@@ -74,7 +78,7 @@ def test_masked_tiles_skipped_with_offsets():
     assert all(it["n0"] == 0 and it["n1"] == 0 for it in its)
     # block entirely in the past: every tile needs all KV tiles, as in non-causal
     its = items(1, 1, 512, 512, 128, True, shift=512)
-    assert all(it["n0"] == 4 and it["n1"] == 4 for it in its)
+    assert all(it["n"] == 4 and it["n0"] == 4 for it in its)
 
 
 def test_total_causal_tiles_is_triangular():
