@@ -6,7 +6,7 @@ NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 PKG       := flash_attention_cuda_b200
 LIB       := $(PKG)/libflashattn_b200.so
 CSRC      := $(PKG)/csrc/fa_api.cu
-CHDR      := $(PKG)/csrc/fa_fwd_sm100.cuh $(PKG)/csrc/sm100_ptx.cuh include/flash_attn.h
+CHDR      := $(PKG)/csrc/fa_fwd_sm100.cuh $(PKG)/csrc/fa_fwd_pair_sm100.cuh $(PKG)/csrc/sm100_ptx.cuh include/flash_attn.h
 
 all: $(LIB) oracle flash_attention
 

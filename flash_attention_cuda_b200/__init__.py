@@ -59,7 +59,8 @@ class KernelInfo(ctypes.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_PKG_DIR, "csrc", f) for f in ("fa_api.cu", "fa_fwd_sm100.cuh", "sm100_ptx.cuh")]
+    srcs = [os.path.join(_PKG_DIR, "csrc", f) for f in ("fa_api.cu", "fa_fwd_sm100.cuh", "fa_fwd_pair_sm100.cuh",
+                                                       "sm100_ptx.cuh")]
     srcs.append(os.path.join(_REPO, "include", "flash_attn.h"))
     if not force and os.path.exists(LIB_PATH):
         if all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs if os.path.exists(s)):
@@ -104,9 +105,9 @@ def lib() -> ctypes.CDLL:
     L.flash_attn_version.restype = ctypes.c_char_p
     L.flash_attn_debug_work_item.argtypes = [ci, ci, ci, ci, ci, ci, ci, ll] + [ctypes.POINTER(ci)] * 5
     L.flash_attn_debug_work_item.restype = ci
-    if hasattr(L, "flash_attn_debug_cta_group"):   # absent from archived A/B builds of older kernels
-        L.flash_attn_debug_cta_group.argtypes = [ci]
-        L.flash_attn_debug_cta_group.restype = ci
+    if hasattr(L, "flash_attn_debug_tiles_per_item"):   # absent from archived A/B builds of older kernels
+        L.flash_attn_debug_tiles_per_item.argtypes = [ci]
+        L.flash_attn_debug_tiles_per_item.restype = ci
     L.flash_attn_debug_status.argtypes = [ctypes.POINTER(ctypes.c_uint)]
     L.flash_attn_debug_status.restype = ci
     _lib = L
@@ -198,6 +199,6 @@ def work_item(w: int, B: int, H: int, Nq: int, Nkv: int, D: int, causal: bool, s
     return {"total": total, "bh": bh, "q0": q0, "n0": n0, "n1": n1, "n": max(n0, n1)}
 
 
-def cta_group(D: int) -> int:
-    """CTAs per work unit for this head_dim: a work item covers cta_group 128-row Q tiles."""
-    return int(lib().flash_attn_debug_cta_group(D))
+def tiles_per_item(D: int) -> int:
+    """128-row Q tiles one work item covers (2 for the default kernel; 1 or 2 for the pair kernel)."""
+    return int(lib().flash_attn_debug_tiles_per_item(D))

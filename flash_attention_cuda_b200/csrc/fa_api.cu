@@ -12,7 +12,8 @@
 #include <cstring>
 #include <mutex>
 
-#include "fa_fwd_sm100.cuh"
+#include "fa_fwd_sm100.cuh"        // default kernel: one CTA per work item, two Q tiles per CTA
+#include "fa_fwd_pair_sm100.cuh"   // experimental CTA-pair kernel (cta_group::2), opt-in
 
 namespace {
 
@@ -53,22 +54,35 @@ void load_encode_fn() {
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
 }
 
-template <int D, int CG>
+template <int D>
 int set_kernel_attrs() {
-    return (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     fa::Cfg<D, CG>::kSmemBytes);
+    return (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fa::Cfg<D>::kSmemBytes);
+}
+template <int D, int CG>
+int set_pair_kernel_attrs() {
+    return (int)cudaFuncSetAttribute(fa_pair::fa_fwd_kernel<D, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fa_pair::Cfg<D, CG>::kSmemBytes);
 }
 
-// CTAs per work unit.  D = 128 runs as CTA pairs (tcgen05.mma.cta_group::2, M = 256); D = 64 keeps
-// one CTA per unit (its V half would be narrower than a 128-byte swizzle panel).  The environment
-// variable FLASH_ATTN_B200_CG=1 forces single CTAs for D = 128 as well (A/B measurements).
-int cta_group_for(int D) {
+// FLASH_ATTN_B200_KERNEL=pair selects the experimental CTA-pair kernel for the whole
+// process; anything else runs the default kernel.  Read once.
+bool use_pair_kernel() {
+    static const bool pair = []() {
+        const char* e = getenv("FLASH_ATTN_B200_KERNEL");
+        return e && strcmp(e, "pair") == 0;
+    }();
+    return pair;
+}
+// CTAs per work unit of the pair kernel: D = 128 runs as CTA pairs (tcgen05.mma.cta_group::2, M = 256);
+// D = 64 keeps one CTA per unit (its V half would be narrower than a 128-byte swizzle panel).
+// FLASH_ATTN_B200_CG=1 forces single CTAs for D = 128 as well (A/B measurements).
+int pair_cta_group_for(int D) {
     static const int forced = []() {
         const char* e = getenv("FLASH_ATTN_B200_CG");
         return (e && e[0] == '1') ? 1 : 0;
     }();
-    if (D == 64 || forced == 1) return 1;
-    return 2;
+    return (D == 64 || forced == 1) ? 1 : 2;
 }
 
 // Per-device one-time setup.  Re-entrant from several host threads (one per GPU in the
@@ -86,9 +100,13 @@ DeviceState* device_state(int* err) {
         st->num_sms = prop.multiProcessorCount;
         st->cc_major = prop.major;
         if (prop.major != 10) { st->ok = FA_ERR_UNSUPPORTED_ARCH; return; }
-        int r = set_kernel_attrs<128, 1>();
-        if (r == 0) r = set_kernel_attrs<128, 2>();
-        if (r == 0) r = set_kernel_attrs<64, 1>();
+        int r = set_kernel_attrs<128>();
+        if (r == 0) r = set_kernel_attrs<64>();
+        if (r == 0 && use_pair_kernel()) {
+            r = set_pair_kernel_attrs<128, 1>();
+            if (r == 0) r = set_pair_kernel_attrs<128, 2>();
+            if (r == 0) r = set_pair_kernel_attrs<64, 1>();
+        }
         if (r == 0) r = (int)cudaMalloc(&st->sched, kSchedSlots * 2 * sizeof(int));
         if (r == 0) r = (int)cudaMemset(st->sched, 0, kSchedSlots * 2 * sizeof(int));
         st->ok = r;
@@ -98,7 +116,7 @@ DeviceState* device_state(int* err) {
 }
 
 // [BH, N, D] fp16, box = 64 halves x `rows` rows x 1 head, 128-byte swizzle; rows past N read as zero
-// and are dropped on store.
+// (and are dropped on a TMA store).
 int make_tmap(CUtensorMap* tm, const void* base, int BH, int N, int D, int rows = fa::kBlockN) {
     std::call_once(g_encode_once, load_encode_fn);
     if (!g_encode) return FA_ERR_TENSORMAP;
@@ -129,9 +147,8 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     if (shift > 0x3fffffffLL) shift = 0x3fffffffLL;
     if (shift < -0x3fffffffLL) shift = -0x3fffffffLL;
     p.shift = (int)shift;
-    p.cg = cta_group_for(D);
-    p.nqu = (Nq + p.cg * fa::kBlockM - 1) / (p.cg * fa::kBlockM);
-    const long long tw = (long long)BH * p.nqu;
+    p.nqp = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
+    const long long tw = (long long)BH * p.nqp;
     p.total_work = (int)tw;
     // heads per scheduling group: K+V of the group <= 64 MB (half of B200's 126 MB L2)
     const long long kv_bytes = 2LL * Nkv * D * 2;
@@ -144,19 +161,58 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     return p;
 }
 
-template <int D, int CG>
+template <int D>
 int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-           const CUtensorMap& to, fa::Params p, cudaStream_t stream) {
-    int units = p.total_work < st->num_sms / CG ? p.total_work : st->num_sms / CG;
-    if (units < 1) units = 1;
+           fa::Params p, cudaStream_t stream) {
+    int grid = p.total_work < st->num_sms ? p.total_work : st->num_sms;
+    if (grid < 1) grid = 1;
     p.sched = st->sched + 2 * (st->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
     // launched with programmatic stream serialization (PDL): the kernel's prologue overlaps the tail
     // of its predecessor in the stream; it executes griddepcontrol.wait before touching global memory
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)(units * CG));
+    cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(fa::kNumThreads);
-    cfg.dynamicSmemBytes = fa::Cfg<D, CG>::kSmemBytes;
+    cfg.dynamicSmemBytes = fa::Cfg<D>::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D>, tq, tk, tv, p);
+    if (le != cudaSuccess) return (int)le;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();   // FA.cu:662
+}
+
+// ---- experimental CTA-pair kernel (fa_fwd_pair_sm100.cuh) ----
+fa_pair::Params make_pair_params(const fa::Params& b, int D) {
+    fa_pair::Params p;
+    memset(&p, 0, sizeof p);
+    p.o = b.o; p.o_partial = b.o_partial; p.ml = b.ml;
+    p.Nq = b.Nq; p.Nkv = b.Nkv; p.BH = b.BH;
+    p.causal = b.causal; p.shift = b.shift;
+    p.cg = pair_cta_group_for(D);
+    p.nqu = (b.Nq + p.cg * fa_pair::kBlockM - 1) / (p.cg * fa_pair::kBlockM);
+    p.total_work = (int)((long long)b.BH * p.nqu);
+    p.group_heads = b.group_heads;
+    p.partial_mode = b.partial_mode; p.accumulate = b.accumulate;
+    p.scale = b.scale; p.scale_log2 = b.scale_log2;
+    return p;
+}
+
+template <int D, int CG>
+int launch_pair(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                const CUtensorMap& to, fa_pair::Params p, cudaStream_t stream) {
+    int units = p.total_work < st->num_sms / CG ? p.total_work : st->num_sms / CG;
+    if (units < 1) units = 1;
+    p.sched = st->sched + 2 * (st->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(units * CG));
+    cfg.blockDim = dim3(fa_pair::kNumThreads);
+    cfg.dynamicSmemBytes = fa_pair::Cfg<D, CG>::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -167,26 +223,40 @@ int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const 
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CG == 2 ? 2 : 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D, CG>, tq, tk, tv, to, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fa_pair::fa_fwd_kernel<D, CG>, tq, tk, tv, to, p);
     if (le != cudaSuccess) return (int)le;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    return (int)cudaGetLastError();   // FA.cu:662
+    return (int)cudaGetLastError();
+}
+
+int run_pair(DeviceState* st, const void* q, const void* k, const void* v, const fa::Params& base, int D,
+             cudaStream_t stream) {
+    fa_pair::Params p = make_pair_params(base, D);
+    if ((long long)p.BH * p.nqu > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
+    CUtensorMap tq, tk, tv, to;
+    int rc;
+    if ((rc = make_tmap(&tq, q, p.BH, p.Nq, D)) != FA_OK) return rc;
+    if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D, fa_pair::kBlockN / p.cg)) != FA_OK) return rc;
+    if ((rc = make_tmap(&tv, v, p.BH, p.Nkv, D)) != FA_OK) return rc;
+    // O store map (unused in partial mode: describe Q's extent on a valid pointer)
+    if ((rc = make_tmap(&to, p.o ? (const void*)p.o : q, p.BH, p.Nq, D)) != FA_OK) return rc;
+    if (D == 64) return launch_pair<64, 1>(st, tq, tk, tv, to, p, stream);
+    return p.cg == 2 ? launch_pair<128, 2>(st, tq, tk, tv, to, p, stream)
+                     : launch_pair<128, 1>(st, tq, tk, tv, to, p, stream);
 }
 
 int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaStream_t stream) {
     int err = 0;
     DeviceState* st = device_state(&err);
     if (!st) return err;
-    if ((long long)p.BH * p.nqu > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
-    CUtensorMap tq, tk, tv, to;
+    if (use_pair_kernel()) return run_pair(st, q, k, v, p, D, stream);
+    if ((long long)p.BH * p.nqp > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
+    CUtensorMap tq, tk, tv;
     int rc;
     if ((rc = make_tmap(&tq, q, p.BH, p.Nq, D)) != FA_OK) return rc;
-    if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D, fa::kBlockN / p.cg)) != FA_OK) return rc;
+    if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D)) != FA_OK) return rc;
     if ((rc = make_tmap(&tv, v, p.BH, p.Nkv, D)) != FA_OK) return rc;
-    // O store map (unused in partial mode, where p.o aliases nothing: describe Q's extent on a valid pointer)
-    if ((rc = make_tmap(&to, p.o ? (const void*)p.o : q, p.BH, p.Nq, D)) != FA_OK) return rc;
-    if (D == 64) return launch<64, 1>(st, tq, tk, tv, to, p, stream);
-    return p.cg == 2 ? launch<128, 2>(st, tq, tk, tv, to, p, stream) : launch<128, 1>(st, tq, tk, tv, to, p, stream);
+    return D == 128 ? launch<128>(st, tq, tk, tv, p, stream) : launch<64>(st, tq, tk, tv, p, stream);
 }
 
 }  // namespace
@@ -272,31 +342,47 @@ int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_att
     if (B < 1 || H < 1 || N < 1) return FA_ERR_BAD_SHAPE;
     memset(info, 0, sizeof *info);
     cudaFuncAttributes attr;
-    const int cg = cta_group_for(D);
-    cudaError_t e = D == 64    ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<64, 1>)
-                    : cg == 2 ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, 2>)
-                              : cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, 1>);
+    cudaError_t e = D == 128 ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128>)
+                             : cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<64>);
     if (e != cudaSuccess) return (int)e;
     int err = 0;
     DeviceState* st = device_state(&err);
     if (!st) return err;
     fa::Params p = make_params(B * H, N, N, D, causal, 0);
+    info->cta_group = 1;
+    if (use_pair_kernel()) {
+        const int cg = pair_cta_group_for(D);
+        e = D == 64    ? cudaFuncGetAttributes(&attr, fa_pair::fa_fwd_kernel<64, 1>)
+            : cg == 2 ? cudaFuncGetAttributes(&attr, fa_pair::fa_fwd_kernel<128, 2>)
+                      : cudaFuncGetAttributes(&attr, fa_pair::fa_fwd_kernel<128, 1>);
+        if (e != cudaSuccess) return (int)e;
+        const fa_pair::Params pp = make_pair_params(p, D);
+        info->regs_per_thread = attr.numRegs;
+        info->local_bytes_per_thread = (int)attr.localSizeBytes;
+        info->static_smem_bytes = (int)attr.sharedSizeBytes;
+        info->dynamic_smem_bytes = D == 64    ? fa_pair::Cfg<64, 1>::kSmemBytes
+                                   : cg == 2 ? fa_pair::Cfg<128, 2>::kSmemBytes
+                                             : fa_pair::Cfg<128, 1>::kSmemBytes;
+        info->threads_per_cta = fa_pair::kNumThreads;
+        int units = pp.total_work < st->num_sms / cg ? pp.total_work : st->num_sms / cg;
+        info->ctas = (units < 1 ? 1 : units) * cg;
+        info->tmem_columns = fa_pair::kTmemCols;
+        info->kv_stages = D == 64    ? fa_pair::Cfg<64, 1>::kKStages + fa_pair::Cfg<64, 1>::kVStages
+                          : cg == 2 ? fa_pair::Cfg<128, 2>::kKStages + fa_pair::Cfg<128, 2>::kVStages
+                                    : fa_pair::Cfg<128, 1>::kKStages + fa_pair::Cfg<128, 1>::kVStages;
+        info->work_items = pp.total_work;
+        info->num_sms = st->num_sms;
+        info->cta_group = cg;
+        return FA_OK;
+    }
     info->regs_per_thread = attr.numRegs;
     info->local_bytes_per_thread = (int)attr.localSizeBytes;
     info->static_smem_bytes = (int)attr.sharedSizeBytes;
-    info->dynamic_smem_bytes = D == 64    ? fa::Cfg<64, 1>::kSmemBytes
-                               : cg == 2 ? fa::Cfg<128, 2>::kSmemBytes
-                                         : fa::Cfg<128, 1>::kSmemBytes;
+    info->dynamic_smem_bytes = D == 128 ? fa::Cfg<128>::kSmemBytes : fa::Cfg<64>::kSmemBytes;
     info->threads_per_cta = fa::kNumThreads;
-    {
-        int units = p.total_work < st->num_sms / cg ? p.total_work : st->num_sms / cg;
-        info->ctas = (units < 1 ? 1 : units) * cg;
-    }
+    info->ctas = p.total_work < st->num_sms ? p.total_work : st->num_sms;
     info->tmem_columns = fa::kTmemCols;
-    info->kv_stages = D == 64    ? fa::Cfg<64, 1>::kKStages + fa::Cfg<64, 1>::kVStages
-                      : cg == 2 ? fa::Cfg<128, 2>::kKStages + fa::Cfg<128, 2>::kVStages
-                                : fa::Cfg<128, 1>::kKStages + fa::Cfg<128, 1>::kVStages;
-    info->cta_group = cg;
+    info->kv_stages = D == 128 ? fa::Cfg<128>::kStages : fa::Cfg<64>::kStages;
     info->work_items = p.total_work;
     info->num_sms = st->num_sms;
     return FA_OK;
@@ -336,7 +422,8 @@ const char* flash_attn_error_string(int code) {
     }
 }
 
-const char* flash_attn_version(void) { return "flashattn_b200 0.2 (sm_100a tcgen05/TMA forward, CTA-pair MMA)"; }
+const char* flash_attn_version(void) { return use_pair_kernel() ? "flashattn_b200 0.2 (sm_100a tcgen05/TMA forward, experimental CTA-pair kernel)"
+                             : "flashattn_b200 0.2 (sm_100a tcgen05/TMA forward)"; }
 
 }  // extern "C"
 
@@ -351,15 +438,17 @@ extern "C" int flash_attn_debug_status(unsigned int* out4) {
 
 #ifdef FA_TIMING
 // debug builds only (-DFA_TIMING): in-kernel clock64 probes, see tests/harness/timing.py
-extern "C" int flash_attn_debug_timing(unsigned long long* out32, int reset) {   // 64 counters
+extern "C" int flash_attn_debug_timing(unsigned long long* out32, int reset) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemcpyFromSymbol(out32, fa::g_timing, 64 * sizeof(unsigned long long));
-    if (e != cudaSuccess) return (int)e;
-    if (reset) {
-        unsigned long long z[64] = {0};
-        e = cudaMemcpyToSymbol(fa::g_timing, z, sizeof z);
+    unsigned long long z[64] = {0};
+    if (use_pair_kernel()) {   // 64 counters
+        e = cudaMemcpyFromSymbol(out32, fa_pair::g_timing_pair, 64 * sizeof(unsigned long long));
+        if (e == cudaSuccess && reset) e = cudaMemcpyToSymbol(fa_pair::g_timing_pair, z, 64 * sizeof(unsigned long long));
+        return (int)e;
     }
+    e = cudaMemcpyFromSymbol(out32, fa::g_timing, 32 * sizeof(unsigned long long));
+    if (e == cudaSuccess && reset) e = cudaMemcpyToSymbol(fa::g_timing, z, 32 * sizeof(unsigned long long));
     return (int)e;
 }
 #endif
@@ -370,11 +459,23 @@ extern "C" int flash_attn_debug_work_item(int w, int B, int H, int Nq, int Nkv, 
                                           int* total, int* bh, int* q0, int* n0, int* n1) {
     if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
     fa::Params p = make_params(B * H, Nq, Nkv, D, causal, shift);
+    if (use_pair_kernel()) {
+        const fa_pair::Params pp = make_pair_params(p, D);
+        *total = pp.total_work;
+        if (w < 0 || w >= pp.total_work) return FA_ERR_BAD_SHAPE;
+        fa_pair::WorkItem it = fa_pair::decode_work(w, pp);
+        *bh = it.bh; *q0 = it.q0; *n0 = it.n0; *n1 = it.n1;
+        return FA_OK;
+    }
     *total = p.total_work;
     if (w < 0 || w >= p.total_work) return FA_ERR_BAD_SHAPE;
     fa::WorkItem it = fa::decode_work(w, p);
     *bh = it.bh; *q0 = it.q0; *n0 = it.n0; *n1 = it.n1;
     return FA_OK;
 }
-// CTAs per work unit for this head_dim (1 or 2): how many 128-row Q tiles a work item covers
-extern "C" int flash_attn_debug_cta_group(int D) { return (D == 64 || D == 128) ? cta_group_for(D) : FA_ERR_BAD_HEAD_DIM; }
+// 128-row Q tiles a work item covers: 2 for the default kernel (one CTA, two tiles); for the pair
+// kernel the CTAs per unit (1 or 2), each holding one tile
+extern "C" int flash_attn_debug_tiles_per_item(int D) {
+    if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+    return use_pair_kernel() ? pair_cta_group_for(D) : 2;
+}

@@ -1,39 +1,33 @@
 // fa_fwd_sm100.cuh -- FlashAttention forward for B200 (sm_100a): persistent, warp-specialised,
-// TMA -> 128B-swizzled smem -> tcgen05.mma with S/P/O in tensor memory ("v9").
+// TMA -> 128B-swizzled smem -> tcgen05.mma with S/P/O in tensor memory.
 //
 // Replaces the reference's device path flash_attention_v9<...> (flash_attention.cu:67-554):
 //   FA.cu:103-112  block->(bh, q-block) mapping, GRID_SWAP    -> persistent work loop, heavy-first
-//   FA.cu:145-159  Q fragments in registers                   -> Q tile resident in smem (TMA), double-buffered
-//   FA.cu:417-447  synchronous K/V tile load + 2 barriers     -> producer warp, separate K and V mbarrier rings
+//   FA.cu:145-159  Q fragments in registers                   -> Q tile pair resident in smem (TMA)
+//   FA.cu:417-447  synchronous K/V tile load + 2 barriers     -> producer warp, mbarrier ring
 //   FA.cu:188-233  DO_QK_MATMUL (mma.sync m16n8k16)           -> tcgen05.mma SS, S in TMEM
 //   FA.cu:235-288  DO_SOFTMAX (quad shuffles, eager rescale)  -> one thread per row, lazy rescale
 //   FA.cu:290-334  DO_PV_MATMUL (P in registers)              -> P fp16 in TMEM, tcgen05.mma TS
-//   FA.cu:497-553  multi-pass smem output staging             -> TMEM -> registers -> swizzled smem -> TMA store
+//   FA.cu:497-553  epilogue via smem                          -> TMEM -> registers -> global
 //   FA.cu:460-496  split-K partial epilogue (dead code there) -> partial mode used by ring CP
 //
-// Work unit = one head x CG consecutive 128-row Q tiles, CG = 1 (one CTA) or 2 (a CTA pair driving
-// tcgen05.mma.cta_group::2 with M = 256: each CTA owns 128 Q rows and supplies half of every K and V
-// tile, so K/V smem fill, smem operand reads and L2 traffic per SM are halved).
+// CTA = 384 threads:  warps 0-3  softmax/correction/epilogue for Q tile 0 (128 rows)
+//                     warps 4-7  same for Q tile 1
+//                     warp 8     TMEM allocator + tcgen05.mma issuer (one lane)
+//                     warp 9     TMA producer (one lane)
+//                     warps 10,11 idle (pad the third warpgroup)
+// One CTA per SM; each CTA loops over work items (bh, pair of 128-row Q tiles).
 //
-// CTA = 384 threads:  warps 0-3  softmax set A: KV tiles with even global index
-//                     warps 4-7  softmax set B: odd tiles -- SAME 128 query rows as set A
-//                     warp 8     TMEM allocator + tcgen05.mma issuer for S = Q K^T (leader CTA only)
-//                     warp 9     TMA producer (Q, K and V tiles) + dynamic tile scheduler
-//                     warp 10    TMA store of finished O tiles
-//                     warp 11    tcgen05.mma issuer for O += P V (leader CTA only)
-// Two issuer warps because one warp's instruction latency (~6 cycles per dependent instruction
-// when it runs alone) made a single issuer the bottleneck at ~280 instructions per tile
-// (profiles/r01_v9d_*); the two MMA streams only meet through mbarriers anyway.
+// TMEM (512 columns x 128 lanes x 32 bit): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).
+// P_t (fp16, two per column) overwrites columns [0,64) of S_t once the owning thread has read
+// its S row, and is handed to the MMA warp in two halves (keys 0-63, 64-127) so that the first four
+// PV k-steps run while the second half of the exponentials is still being computed.
+// Tensor-pipe order per KV tile j:  PV0(j) QK0(j+1) PV1(j) QK1(j+1), so each softmax warpgroup works
+// on S_t(j+1) while the tensor core runs the other tile's two MMAs.
 //
-// TMEM (512 columns x 128 lanes x 32 bit):  S_a [0,128)  S_b [128,256)  P_a [256,320)  P_b [320,384)
-//                                           O [384,384+D)
-// S and P do not alias, and each S buffer belongs to one softmax set, so the tensor pipe never waits
-// for a whole S -> P -> PV -> QK round trip of one tile (the limiter of the previous two-Q-tile
-// design, profiles/r01_v4_*): QK(g+2) is issued as soon as set (g&1) has READ S(g) into registers,
-// PV(g) as soon as P(g) lands, and the two sets run their softmax of consecutive tiles concurrently.
-// Because both sets feed one O accumulator they share one lazily-updated reference max per row:
-// a set publishes its m_ref after every tile (smem + mbarrier, per 32-row quadrant) and the other
-// set picks it up before deciding its own; partial row sums are merged in the epilogue.
+// Why not 64-wide KV sub-tiles with S double-buffered (tried, profiles/r01_v3_subtile_*): QK^T with
+// N=64 in SS mode re-reads the Q slice from shared memory for half the math (192 B/clk > the 128 B/clk
+// smem port).  N=128 sits exactly at the port limit, so the S->P->PV->QK chain is shortened instead.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -48,85 +42,49 @@ namespace fa {
 
 using namespace sm100;
 
-constexpr int kBlockM = 128;      // Q rows per CTA tile (UMMA M per CTA)
+constexpr int kBlockM = 128;      // Q rows per tile  (UMMA M)
 constexpr int kBlockN = 128;      // K/V rows per tile (UMMA N of QK^T, K extent of PV)
 constexpr int kNumThreads = 384;
 constexpr int kMmaWarp = 8;
 constexpr int kLoadWarp = 9;
-constexpr int kStoreWarp = 10;
-constexpr int kPvWarp = 11;
 constexpr int kTmemCols = 512;
 constexpr int kRegsSoftmax = 208;   // setmaxnreg: softmax warpgroups grow, the producer/MMA warpgroup shrinks
 constexpr int kRegsOther = 80;      // 2*128*208 + 128*80 = 63488 <= 168 (launch) * 384
-constexpr float kRescaleThreshold = 8.0f;   // lazy rescale: tolerate P up to 2^8 before moving the reference max
+constexpr float kRescaleThreshold = 8.0f;
 // Of every 4 element pairs, this many take exp2 on the FMA pipe (Cody-Waite + degree-3 minimax)
 // instead of MUFU.EX2: at 16 MUFU/clk/SM the 16384 exponentials of a 128x128 tile cost as many
 // cycles as its two MMAs, so the SFU -- not the tensor core -- would set the pace.
-#ifndef FA_ANTIPHASE
-#define FA_ANTIPHASE 0
-#endif
 #ifndef FA_POLY_PAIRS
 #define FA_POLY_PAIRS 1
 #endif
-constexpr int kPolyPairs = FA_POLY_PAIRS;
+constexpr int kPolyPairs = FA_POLY_PAIRS;  // lazy rescale: tolerate P up to 2^8 before moving the reference max
 
-template <int D, int CG>
+template <int D>
 struct Cfg {
     static_assert(D == 64 || D == 128, "head_dim must be 64 or 128");
-    static_assert(CG == 1 || CG == 2, "CTA group size is 1 or 2");
-    static_assert(D / CG >= 64, "the V half of a CTA pair must be at least one 128-byte panel wide");
-    static constexpr int kPanels = D / 64;                      // 128-byte swizzle panels per Q/K row
-    static constexpr int kQPanelBytes = kBlockM * 128;          // 128 rows x 128 B
-    static constexpr int kQTileBytes = kPanels * kQPanelBytes;
-    static constexpr int kKRows = kBlockN / CG;                 // keys of a tile this CTA loads
-    static constexpr int kKPanelBytes = kKRows * 128;
-    static constexpr int kKBytes = kPanels * kKPanelBytes;      // ring entry: this CTA's part of a K tile
-    static constexpr int kVPanels = D / (64 * CG);              // this CTA's d-columns of V, in panels
-    static constexpr int kVPanelBytes = kBlockN * 128;
-    static constexpr int kVBytes = kVPanels * kVPanelBytes;     // ring entry: this CTA's part of a V tile
-    static constexpr int kKStages = (D == 128) ? (CG == 1 ? 2 : 4) : 5;
-    static constexpr int kVStages = (D == 128) ? (CG == 1 ? 2 : 5) : 6;
-    static constexpr int kOffK = 2 * kQTileBytes;               // Q is double-buffered (and stages O)
-    static constexpr int kOffV = kOffK + kKStages * kKBytes;
-    static constexpr int kOffBar = kOffV + kVStages * kVBytes;
-    // barrier slots (8 B each)
-    static constexpr int kBarQFull = 0;                          // [2]   leader
-    static constexpr int kBarQEmpty = kBarQFull + 2;             // [2]   per CTA
-    static constexpr int kBarKFull = kBarQEmpty + 2;             // [kKStages] leader
-    static constexpr int kBarKEmpty = kBarKFull + kKStages;      // per CTA
-    static constexpr int kBarVFull = kBarKEmpty + kKStages;      // [kVStages] leader
-    static constexpr int kBarVEmpty = kBarVFull + kVStages;      // per CTA
-    static constexpr int kBarSFull = kBarVEmpty + kVStages;      // [2]   per CTA (multicast commit)
-    static constexpr int kBarSFree = kBarSFull + 2;              // [2]   leader
-    static constexpr int kBarPFull = kBarSFree + 2;              // [2][2] leader, index 2*b + half
-    static constexpr int kBarPvDone = kBarPFull + 4;             // [2]   per CTA (multicast commit)
-    static constexpr int kBarOFree = kBarPvDone + 2;             // [1]   leader
-    static constexpr int kBarOStaged = kBarOFree + 1;            // [1]   per CTA
-    static constexpr int kBarMReady = kBarOStaged + 1;           // [2][4] per CTA, index 4*set + quadrant
-    static constexpr int kBarSchedFull = kBarMReady + 8;         // [2]   per CTA
-    static constexpr int kBarSchedEmpty = kBarSchedFull + 2;     // [2]   leader
-    static constexpr int kNumBars = kBarSchedEmpty + 2;
-    static constexpr int kOffMisc = kOffBar + kNumBars * 8;      // tmem slot (4) + pad (4) + mailbox 2 x int
-    static constexpr int kOffMref = (kOffMisc + 16 + 15) & ~15;  // float [2 sets][128 rows]
-    static constexpr int kOffFin = kOffMref + 2 * kBlockM * 4;   // float2 [2 parities][2 sets][128 rows]
-    static constexpr int kSmemBytes = kOffFin + 2 * 2 * kBlockM * 8;
-    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
-    static constexpr int kTmemS = 0, kTmemP = 256, kTmemO = 384;   // S_b at kTmemS + 128 b, P_b at kTmemP + 64 b
-    static constexpr uint32_t kIdescQK = umma_idesc_f16(kBlockM * CG, kBlockN, 0, 0);
-    static constexpr uint32_t kIdescPV = umma_idesc_f16(kBlockM * CG, D, 0, 1);  // V is MN-major ([kv][d], d contiguous)
-    static constexpr int kSchedConsumers = CG == 1 ? 11 : 21;   // leader: 8 softmax warps + store warp + 2 MMA warps; peer: 8 + store + its producer
+    static constexpr int kPanels = D / 64;                 // 128-byte swizzle panels per row
+    static constexpr int kPanelBytes = 128 * 128;          // 128 rows x 128 B
+    static constexpr int kTileBytes = kPanels * kPanelBytes;
+    static constexpr int kStages = (D == 128) ? 5 : 8;     // K/V ring entries (one tile each)
+    static constexpr int kSmemQ = 2 * kTileBytes;
+    static constexpr int kSmemKV = kStages * kTileBytes;
+    static constexpr int kBarOffset = kSmemQ + kSmemKV;
+    static constexpr int kNumBars = 2 + 2 * kStages + 8 + 4;
+    static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 32 + 1024;  // +32: tmem slot, scheduler slots; +1024: manual alignment slack
+    static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
+    static constexpr uint32_t kIdescQK = umma_idesc_f16(kBlockM, kBlockN, 0, 0);
+    static constexpr uint32_t kIdescPV = umma_idesc_f16(kBlockM, D, 0, 1);  // V is MN-major ([kv][d], d contiguous)
 };
 
 struct Params {
+    __half* o;          // fp16 output [BH, Nq, D]            (partial_mode == 0)
     float* o_partial;   // fp32 un-normalised [BH*Nq, D]       (partial_mode == 1; FA.cu:460-496 format)
     float* ml;          // (m, l) pairs [BH*Nq, 2]
-    __half* o;          // fp16 output [BH, Nq, D]: only used for rows without any visible key (zeros)
     int Nq, Nkv, BH;
     int causal;
     int shift;          // q_offset - kv_offset: key c visible to query r iff c <= r + shift
-    int cg;             // CTAs per work unit (1 or 2)
-    int nqu;            // work units per head = ceil(Nq / (128 * cg))
-    int total_work;     // BH * nqu
+    int nqp;            // Q tile pairs per head = ceil(Nq / 256)
+    int total_work;     // BH * nqp
     int group_heads;    // heads per scheduling group (their K/V working set is sized to stay in L2)
     int partial_mode;
     int accumulate;
@@ -137,9 +95,8 @@ struct Params {
 
 // ---- work decomposition (shared by host tests and every warp role) ----
 struct WorkItem {
-    int bh, q0;      // head index, first local query row of the unit
-    int n0, n1;      // KV tiles the unit's Q tiles need (0 = nothing visible / tile absent); n1 = 0 when cg == 1
-    int n;           // KV tiles the unit streams = max(n0, n1)
+    int bh, q0;      // head index, first local query row of the pair
+    int n0, n1;      // KV tiles the two Q tiles need (0 = nothing visible / tile absent)
 };
 __host__ __device__ inline int kv_trip_count(int q_start, int Nq, int Nkv, int causal, int shift) {
     if (q_start >= Nq) return 0;
@@ -153,43 +110,27 @@ __host__ __device__ inline int kv_trip_count(int q_start, int Nq, int Nkv, int c
     return (int)((vis + kBlockN - 1) / kBlockN);
 }
 // Work order (replaces GRID_SWAP / reversed q-blocks, FA.cu:103-112).  Heads are taken in groups whose
-// K/V fit comfortably in L2; inside a group the order is heaviest Q unit first ACROSS the group's
-// heads (causal: the last unit sees the most keys), so the dynamic scheduler hands out long items
+// K/V fit comfortably in L2; inside a group the order is heaviest Q pair first ACROSS the group's
+// heads (causal: the last pair sees the most keys), so the dynamic scheduler hands out long items
 // early and the tail of the launch is made of the lightest ones, while the CTAs running at any moment
 // still share a few heads' K/V through L2.
 __host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
     WorkItem it;
-    const int per_group = p.group_heads * p.nqu;
+    const int per_group = p.group_heads * p.nqp;
     const int g = w / per_group;
     const int r = w - g * per_group;
     int heads = p.BH - g * p.group_heads;
     if (heads > p.group_heads) heads = p.group_heads;
-    const int u = p.nqu - 1 - r / heads;
+    const int qp = p.nqp - 1 - r / heads;
     it.bh = g * p.group_heads + r % heads;
-    it.q0 = u * p.cg * kBlockM;
+    it.q0 = qp * 2 * kBlockM;
     it.n0 = kv_trip_count(it.q0, p.Nq, p.Nkv, p.causal, p.shift);
-    it.n1 = p.cg == 2 ? kv_trip_count(it.q0 + kBlockM, p.Nq, p.Nkv, p.causal, p.shift) : 0;
-    it.n = it.n0 > it.n1 ? it.n0 : it.n1;
+    it.n1 = kv_trip_count(it.q0 + kBlockM, p.Nq, p.Nkv, p.causal, p.shift);
     return it;
 }
 
 #ifdef FA_TIMING
-__device__ unsigned long long g_timing[64];
-// phase probe: accumulates clock deltas of one sampled warp into g_timing[base + i]
-#define FA_PROBE_DECL long long _pt = clock64(); const bool _ps = (threadIdx.x == 0) && ((gk & 7u) == 3u);
-#define FA_PROBE(i) { const long long _n = clock64(); if (_ps) atomicAdd(&g_timing[32 + (i)], (unsigned long long)(_n - _pt)); _pt = _n; }
-#ifdef FA_TIMING_MMA   // distorts the MMA warp (an atomic per probe): separate switch
-#define FA_MPROBE_DECL long long _mt = clock64();
-#define FA_MPROBE(i) { const long long _n = clock64(); if (lane == 0) atomicAdd(&g_timing[48 + (i)], (unsigned long long)(_n - _mt)); _mt = _n; }
-#else
-#define FA_MPROBE_DECL
-#define FA_MPROBE(i)
-#endif
-#else
-#define FA_PROBE_DECL
-#define FA_PROBE(i)
-#define FA_MPROBE_DECL
-#define FA_MPROBE(i)
+__device__ unsigned long long g_timing[32];
 #endif
 
 struct Ring {
@@ -258,48 +199,17 @@ __device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64
     }
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// Everything a softmax thread needs to know about where things live.
-struct SoftmaxCtx {
-    uint32_t tS, tP, tO;            // TMEM addresses of this set's S / P buffer and of O, lane field included
-    uint32_t bar_s_free;            // leader's (shared::cluster address when CG == 2)
-    uint32_t bar_p_full;            // leader's, + 8 * half
-    uint32_t bar_pv_done_mine;      // local: the PV that read this set's P buffer has retired
-    uint32_t bar_pv_done_other;     // local: same for the other set's buffer
-    uint32_t bar_m_ready_mine;      // local, this warp's quadrant
-    uint32_t bar_m_ready_other;
-    float* mref_mine;               // &mref[set][row]
-    const float* mref_other;        // &mref[1-set][row]
-};
-
-template <int CG>
-__device__ __forceinline__ void arrive_leader(uint32_t bar) {
-    if (CG == 1) mbar_arrive(bar);
-    else mbar_arrive_cluster(bar);
-}
-
 // ---- softmax of one 128x128 S tile; one thread owns one row ----
-//   gk     = index of this tile among the tiles of this set's buffers (global tile index >> 1)
-//   first  = first KV tile of the work unit (no running state yet)
-template <int D, int CG, bool kMask>
-__device__ __forceinline__ void softmax_tile(const Params& p, const SoftmaxCtx& c, int lim_local, bool first,
-                                             uint32_t gk, uint32_t g_prev_k, float& m_ref, float& l_run) {
-    FA_PROBE_DECL
+template <int D, bool kMask>
+__device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
+                                             uint32_t bar_o_full, int lim_local, bool have_o,
+                                             uint32_t pv_count, float& m_ref, float& l_run) {
     uint32_t s[kBlockN];
-    tmem_ld_x32(c.tS + 0, s + 0);
-    tmem_ld_x32(c.tS + 32, s + 32);
-    tmem_ld_x32(c.tS + 64, s + 64);
-    tmem_ld_x32(c.tS + 96, s + 96);
+    tmem_ld_x32(tS + 0, s + 0);
+    tmem_ld_x32(tS + 32, s + 32);
+    tmem_ld_x32(tS + 64, s + 64);
+    tmem_ld_x32(tS + 96, s + 96);
     tmem_wait_ld();
-    // S is in registers: the tensor core may overwrite this buffer with the tile after next
-    tc_fence_before();
-    __syncwarp();
-    if (lane_id() == 0) arrive_leader<CG>(c.bar_s_free);
-    FA_PROBE(0)
 
     if (kMask) {
 #pragma unroll
@@ -320,37 +230,22 @@ __device__ __forceinline__ void softmax_tile(const Params& p, const SoftmaxCtx& 
         mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
     }
     const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-    FA_PROBE(1)
-
-    // The other set handled the previous tile of this row: adopt its reference max (it has already
-    // rescaled O; only this set's partial row sum has to follow).
-    if (!first) {
-#if FA_ANTIPHASE != 1
-        mbar_wait(c.bar_m_ready_other, g_prev_k & 1u, 24);
-#endif
-        const float m_prev = *reinterpret_cast<const volatile float*>(c.mref_other);
-        if (m_prev > m_ref) {
-            l_run = (m_ref == -INFINITY) ? 0.f : l_run * ex2_approx((m_ref - m_prev) * p.scale_log2);
-            m_ref = m_prev;
-        }
-    }
-    FA_PROBE(2)
     const float m_new = fmaxf(m_ref, m_tile);
 
     // Lazy rescale (replaces the reference's every-tile O *= alpha, FA.cu:267-270): the reference
     // max only moves when the true max has outgrown it by 2^kRescaleThreshold.
     const bool need = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;  // NaN (-inf - -inf) -> false
     if (__any_sync(0xffffffffu, need)) {
-        if (!first) {
+        if (have_o) {
             const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
             const uint64_t alpha2 = pack_f32x2(alpha, alpha);
-            // O holds PV(0..g-1); the last of them (issued from the other set's P) must have retired
-            mbar_wait(c.bar_pv_done_other, g_prev_k & 1u, 40);
+            // O_t holds PV(0..j-1); the last of them must have retired before we touch it
+            mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 40);
             tc_fence_after();
 #pragma unroll
-            for (int cc = 0; cc < D; cc += 32) {
+            for (int c = 0; c < D; c += 32) {
                 uint32_t o[32];
-                tmem_ld_x32(c.tO + cc, o);
+                tmem_ld_x32(tO + c, o);
                 tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
@@ -359,21 +254,12 @@ __device__ __forceinline__ void softmax_tile(const Params& p, const SoftmaxCtx& 
                     o[i] = __float_as_uint(lo);
                     o[i + 1] = __float_as_uint(hi);
                 }
-                tmem_st_x32(c.tO + cc, o);
+                tmem_st_x32(tO + c, o);
             }
-            tmem_wait_st();
             l_run *= alpha;
         }
         m_ref = m_new;
     }
-    // publish the reference max this row now uses (with FA_ANTIPHASE the other set is released only
-    // after the first half of P has gone out -- see the note in the softmax loop)
-    *reinterpret_cast<volatile float*>(c.mref_mine) = m_ref;
-#if !FA_ANTIPHASE
-    __syncwarp();
-    if (lane_id() == 0) mbar_arrive(c.bar_m_ready_mine);
-#endif
-    FA_PROBE(3)
 
     const float m_used = (m_ref == -INFINITY) ? 0.0f : m_ref;
     const float neg = -m_used * p.scale_log2;
@@ -381,61 +267,48 @@ __device__ __forceinline__ void softmax_tile(const Params& p, const SoftmaxCtx& 
     const uint64_t neg2 = pack_f32x2(neg, neg);
     uint64_t sum_a = 0ull, sum_b = 0ull;     // (0.f, 0.f)
     uint32_t pk[32];
-    // P (fp16 A operand of PV) goes to this set's own 64-column buffer in two halves:
+    // P_t (fp16 A operand of PV) overwrites columns [0,64) of S_t, delivered in two halves:
     // keys 0-63 -> columns [0,32) -> barrier half 0, keys 64-127 -> columns [32,64) -> half 1
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         exp_half(s + 64 * h, pk, scale2, neg2, sum_a, sum_b);
-        FA_PROBE(4 + 3 * h)
-        if (h == 0 && gk > 0) {
-            // the PV that consumed this buffer's previous contents has retired (long ago, normally)
-            mbar_wait(c.bar_pv_done_mine, (gk - 1u) & 1u, 41);
-            tc_fence_after();
-        }
-        FA_PROBE(5 + 3 * h)
-        tmem_st_x32(c.tP + 32 * h, pk);
+        tmem_st_x32(tS + 32 * h, pk);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane_id() == 0) {
-            arrive_leader<CG>(c.bar_p_full + 8 * h);   // one arrival per warp
-#if FA_ANTIPHASE
-            if (h == 0) mbar_arrive(c.bar_m_ready_mine);
-#endif
-        }
-        FA_PROBE(6 + 3 * h)
+        if (lane_id() == 0) mbar_arrive(bar_p_full + 8 * h);   // one arrival per warp (barrier count 4)
     }
     float a0, a1;
     unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
     l_run += a0 + a1;
 }
 
-template <int D, int CG>
+template <int D>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
-    using C = Cfg<D, CG>;
-    // SWIZZLE_128B tiles need 1024-byte alignment; no static shared memory is declared, so the
-    // dynamic window starts at the CTA's (1024-aligned) shared base
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t smem_base = smem_u32(smem_raw);
+              const __grid_constant__ CUtensorMap tmV, const Params p) {
+    using C = Cfg<D>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sQ = smem_base;
-    const uint32_t sK = smem_base + C::kOffK;
-    const uint32_t sV = smem_base + C::kOffV;
-    const uint32_t bars = smem_base + C::kOffBar;
-    auto bar = [&](int slot) -> uint32_t { return bars + 8u * (uint32_t)slot; };
-    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + C::kOffMisc);
-    volatile int* sched_w = reinterpret_cast<volatile int*>(smem_raw + C::kOffMisc + 8);   // [2]
-    float* mref = reinterpret_cast<float*>(smem_raw + C::kOffMref);                        // [2][128]
-    float2* fin = reinterpret_cast<float2*>(smem_raw + C::kOffFin);                        // [2][2][128]
+    const uint32_t sKV = smem_base + C::kSmemQ;
+    const uint32_t bars = smem_base + C::kBarOffset;
+    const uint32_t bar_q_full = bars + 0;
+    const uint32_t bar_q_empty = bars + 8;
+    const uint32_t bar_kv_full = bars + 16;                       // [kStages]
+    const uint32_t bar_kv_empty = bar_kv_full + 8 * C::kStages;   // [kStages]
+    const uint32_t bar_s_full = bar_kv_empty + 8 * C::kStages;    // [tile]
+    const uint32_t bar_p_full = bar_s_full + 16;                  // [tile][half]  index 2*t + h
+    const uint32_t bar_o_full = bar_p_full + 32;                  // [tile]
+    const uint32_t bar_sched_full = bar_o_full + 16;              // [2] work-index slots, producer -> everyone
+    const uint32_t bar_sched_empty = bar_sched_full + 16;         // [2]
+    const uint32_t tmem_slot = bar_sched_empty + 16;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    volatile int* sched_w = reinterpret_cast<volatile int*>(tmem_slot_ptr + 2);   // [2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
-    const bool leader = rank == 0u;
-    // address of the leader CTA's copy of a barrier / mailbox word of this CTA
-    const uint32_t lead_delta = (CG == 2) ? (mapa_shared(smem_base, 0u) - smem_base) : 0u;
-    auto lbar = [&](int slot) -> uint32_t { return bar(slot) + lead_delta; };
 #ifdef FA_TIMING
     long long k_c0 = 0;
     unsigned long long k_t0 = 0;
@@ -446,56 +319,35 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #endif
 
     if (threadIdx.x == 0) {
-        if ((smem_base & 1023u) != 0u && atomicExch(&g_watchdog[0], 1u) == 0u) {
-            g_watchdog[1] = 99u;   // misaligned dynamic shared memory: results are garbage, the host reports it
-            g_watchdog[2] = blockIdx.x;
-            g_watchdog[3] = smem_base;
+        mbar_init(bar_q_full, 1);
+        mbar_init(bar_q_empty, 1);
+        for (int i = 0; i < C::kStages; i++) {
+            mbar_init(bar_kv_full + 8 * i, 1);
+            mbar_init(bar_kv_empty + 8 * i, 1);
+        }
+        for (int t = 0; t < 2; t++) {
+            mbar_init(bar_s_full + 8 * t, 1);
+            mbar_init(bar_p_full + 16 * t, 4);        // one arrival per softmax warp of the tile,
+            mbar_init(bar_p_full + 16 * t + 8, 4);    // per half of P
+            mbar_init(bar_o_full + 8 * t, 1);
         }
         for (int i = 0; i < 2; i++) {
-            mbar_init(bar(C::kBarQFull + i), 1);
-            mbar_init(bar(C::kBarQEmpty + i), 2);                  // last QK^T retired + O tile stored
-            mbar_init(bar(C::kBarSFull + i), 1);
-            mbar_init(bar(C::kBarSFree + i), 4 * CG);              // one arrival per softmax warp of the set
-            mbar_init(bar(C::kBarPFull + 2 * i), 4 * CG);
-            mbar_init(bar(C::kBarPFull + 2 * i + 1), 4 * CG);
-            mbar_init(bar(C::kBarPvDone + i), 1);
-            mbar_init(bar(C::kBarSchedFull + i), 1);
-            mbar_init(bar(C::kBarSchedEmpty + i), C::kSchedConsumers);
+            mbar_init(bar_sched_full + 8 * i, 1);
+            mbar_init(bar_sched_empty + 8 * i, 9);    // MMA warp + 8 softmax warps
         }
-        for (int i = 0; i < C::kKStages; i++) {
-            mbar_init(bar(C::kBarKFull + i), 1);
-            mbar_init(bar(C::kBarKEmpty + i), 1);
-        }
-        for (int i = 0; i < C::kVStages; i++) {
-            mbar_init(bar(C::kBarVFull + i), 1);
-            mbar_init(bar(C::kBarVEmpty + i), 1);
-        }
-        mbar_init(bar(C::kBarOFree), 8 * CG);
-        mbar_init(bar(C::kBarOStaged), 8);
-        for (int i = 0; i < 8; i++) mbar_init(bar(C::kBarMReady + i), 1);
         fence_mbar_init();
     }
     if (warp == kMmaWarp) {
-        if (CG == 1) {
-            tmem_alloc(smem_u32(tmem_slot_ptr), kTmemCols);
-            tmem_relinquish();
-        } else {
-            tmem_alloc_2sm(smem_u32(tmem_slot_ptr), kTmemCols);
-            tmem_relinquish_2sm();
-        }
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
     }
     if (warp == kLoadWarp && lane == 0) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
-        tma_prefetch_desc(&tmO);
     }
     tc_fence_before();
     __syncthreads();
-    if (CG == 2) {   // the peer's barriers must be initialised before anything arrives on them
-        cluster_arrive_release();
-        cluster_wait_acquire();
-    }
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -506,252 +358,193 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // Dynamic tile scheduler (replaces the reference's static blockIdx mapping, FA.cu:103-112): the
-    // leader's producer warp claims work indices (first one static, the rest from a global counter)
-    // and publishes them through a 2-slot smem mailbox (in both CTAs of a pair); every consumer warp
-    // reads slot i&1 for its i-th unit.  Returns -1 when the grid has run out of work.
+    // producer warp claims work indices (first one static, the rest from a global counter) and
+    // publishes them through a 2-slot smem mailbox; every consumer warp reads slot i&1 for its i-th
+    // item.  Work order is heads-outermost, heaviest Q pair first (decode_work), so the causal tail is
+    // made of the lightest items.  Returns -1 when the grid has run out of work.
     auto next_work = [&](uint32_t i) -> int {
         const uint32_t slot = i & 1u;
-        if (CG == 1) mbar_wait(bar(C::kBarSchedFull + slot), (i >> 1) & 1u, 50);
-        else mbar_wait_cluster(bar(C::kBarSchedFull + slot), (i >> 1) & 1u, 50);
+        mbar_wait(bar_sched_full + 8 * slot, (i >> 1) & 1u, 50);
         const int w = sched_w[slot];
         __syncwarp();
-        if (lane == 0) arrive_leader<CG>(lbar(C::kBarSchedEmpty + slot));
+        if (lane == 0) mbar_arrive(bar_sched_empty + 8 * slot);
         return w;
     };
-    // barriers the peer CTA arrives on too; what they guard travels through TMEM / the async proxy
-    auto wait_lead = [&](uint32_t b, uint32_t parity, int tag) { mbar_wait(b, parity, tag); };
 
     // The producer and MMA warps run their loops converged (all 32 lanes take the same branches
     // and waits); the instructions with side effects sit under elect_one().  Warp-uniform control
-    // flow keeps descriptors and barrier addresses in uniform registers.
+    // flow keeps descriptors and barrier addresses in uniform registers -- in a lane-divergent
+    // region every UTCHMMA costs an extra ELECT / R2UR.BROADCAST sequence and the single issuing
+    // thread becomes the bottleneck of the whole CTA (profiles/r01_v1_full_n8192_summary.txt).
     if (warp >= 8) {
     setmaxnreg_dec<kRegsOther>();   // each role's code must be dominated by its own setmaxnreg
     if (warp == kLoadWarp) {
-        // =============================== TMA producer (Q, K, V) + scheduler ===============================
-        Ring rk{0u, 0u}, rv{0u, 0u};
-        const uint32_t num_units = gridDim.x / CG;     // CTAs (pairs) in flight
-        const uint32_t unit_id = blockIdx.x / CG;
+        // =============================== TMA producer ===============================
+        Ring ring{0u, 0u};
         for (uint32_t it = 0;; ++it) {
+            // claim the next work item and publish it
             const uint32_t slot = it & 1u;
+            mbar_wait(bar_sched_empty + 8 * slot, ((it >> 1) & 1u) ^ 1u, 3);
             int w = 0;
-            if (leader) {
-                // claim the next work unit and publish it
-                wait_lead(bar(C::kBarSchedEmpty + slot), ((it >> 1) & 1u) ^ 1u, 3);
-                if (lane == 0) w = (it == 0) ? (int)unit_id : (int)num_units + atomicAdd(p.sched, 1);
-                w = __shfl_sync(0xffffffffu, w, 0);
-                if (w >= p.total_work) w = -1;
-                if (lane == 0) {
-                    sched_w[slot] = w;
-                    mbar_arrive(bar(C::kBarSchedFull + slot));   // release: the slot write is visible to waiters
-                    if (CG == 2) {
-                        st_shared_cluster_u32(mapa_shared(smem_u32(const_cast<int*>(sched_w + slot)), 1u), (uint32_t)w);
-                        mbar_arrive_cluster_release(mapa_shared(bar(C::kBarSchedFull + slot), 1u));
-                    }
-                }
-                __syncwarp();
-            } else {
-                w = next_work(it);
-            }
-            if (w < 0) break;
-            const WorkItem wi = decode_work(w, p);
-            const uint32_t qslot = it & 1u;
-            auto load = [&](uint32_t dst, const CUtensorMap* tm, uint32_t full, int c0, int c1) {
-                if (CG == 1) tma_load_3d(dst, tm, full, c0, c1, wi.bh);
-                else tma_load_3d_2sm(dst, tm, full, c0, c1, wi.bh);
-            };
-            // Q tile of this CTA: the slot is free once the QK^T MMAs of the unit two back have retired
-            // and its O tile (staged in the same buffer) has been read by the TMA store
-            mbar_wait(bar(C::kBarQEmpty + qslot), ((it >> 1) & 1u) ^ 1u, 1);
-            if (elect_one()) {
-                if (leader) mbar_arrive_expect_tx(bar(C::kBarQFull + qslot), CG * C::kQTileBytes);
-#pragma unroll
-                for (int pn = 0; pn < C::kPanels; pn++)
-                    load(sQ + qslot * C::kQTileBytes + pn * C::kQPanelBytes, &tmQ, lbar(C::kBarQFull + qslot), pn * 64,
-                         wi.q0 + (int)rank * kBlockM);
+            if (lane == 0) w = (it == 0) ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(p.sched, 1);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w >= p.total_work) w = -1;
+            if (lane == 0) {
+                sched_w[slot] = w;
+                mbar_arrive(bar_sched_full + 8 * slot);   // release: the slot write is visible to waiters
             }
             __syncwarp();
-            for (int j = 0; j < wi.n; j++) {
-                // K_j: this CTA's kKRows keys
-                mbar_wait(bar(C::kBarKEmpty + rk.idx), rk.phase ^ 1u, 2);
-                if (elect_one()) {
-                    if (leader) mbar_arrive_expect_tx(bar(C::kBarKFull + rk.idx), CG * C::kKBytes);
-#pragma unroll
+            if (w < 0) break;
+            const WorkItem wi = decode_work(w, p);
+            const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
+            const bool have_q1 = wi.q0 + kBlockM < p.Nq;
+            mbar_wait(bar_q_empty, (it & 1u) ^ 1u, 1);   // previous item's QK^T MMAs retired
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_q_full, (have_q1 ? 2 : 1) * C::kTileBytes);
+                for (int t = 0; t < (have_q1 ? 2 : 1); t++)
                     for (int pn = 0; pn < C::kPanels; pn++)
-                        load(sK + rk.idx * C::kKBytes + pn * C::kKPanelBytes, &tmK, lbar(C::kBarKFull + rk.idx), pn * 64,
-                             j * kBlockN + (int)rank * C::kKRows);
-                }
-                __syncwarp();
-                rk.advance<C::kKStages>();
-                // V_j: this CTA's D/CG columns.  K and V have separate rings and separate consumers
-                // (the two issuer warps), so this wait can only delay later loads, never deadlock.
-                mbar_wait(bar(C::kBarVEmpty + rv.idx), rv.phase ^ 1u, 4);
-                if (elect_one()) {
-                    if (leader) mbar_arrive_expect_tx(bar(C::kBarVFull + rv.idx), CG * C::kVBytes);
-#pragma unroll
-                    for (int pn = 0; pn < C::kVPanels; pn++)
-                        load(sV + rv.idx * C::kVBytes + pn * C::kVPanelBytes, &tmV, lbar(C::kBarVFull + rv.idx),
-                             (int)rank * (D / CG) + pn * 64, j * kBlockN);
-                }
-                __syncwarp();
-                rv.advance<C::kVStages>();
+                        tma_load_3d(sQ + t * C::kTileBytes + pn * C::kPanelBytes, &tmQ, bar_q_full, pn * 64,
+                                    wi.q0 + t * kBlockM, wi.bh);
             }
-        }
-    } else if (warp == kMmaWarp && leader) {
-        // =============================== tcgen05.mma issuer: S_b = Q K_j^T ===============================
-        // Runs as far ahead as the two S buffers allow: QK(g) goes out as soon as K_g has landed and
-        // the softmax set of tile g-2 has pulled S(g-2) into registers.
-        Ring rk{0u, 0u};
-        uint32_t gq = 0;                                   // global tile index
-        const uint64_t qdesc0 = umma_smem_desc(sQ, 16, 1024);
-        const uint64_t kdesc0 = umma_smem_desc(sK, 16, 1024);
-        for (uint32_t it = 0;; ++it) {
-            const int w = next_work(it);
-            if (w < 0) break;
-            const WorkItem wi = decode_work(w, p);
-            const uint32_t qslot = it & 1u;
-            mbar_wait(bar(C::kBarQFull + qslot), (it >> 1) & 1u, 10);
-            const uint64_t qdesc = qdesc0 + (uint64_t)((qslot * C::kQTileBytes) >> 4);
-            if (wi.n == 0) {                               // nothing will read this Q tile
-                if (elect_one()) {
-                    if (CG == 1) umma_commit(bar(C::kBarQEmpty + qslot));
-                    else umma_commit_2sm(bar(C::kBarQEmpty + qslot));
-                }
-                __syncwarp();
-            }
-            for (int j = 0; j < wi.n; j++) {
-                const uint32_t b = gq & 1u, k = gq >> 1;
-                mbar_wait(bar(C::kBarKFull + rk.idx), rk.phase, 11);
-                if (k > 0) mbar_wait(bar(C::kBarSFree + b), (k - 1u) & 1u, 12);   // the set has read S_b(previous)
-                tc_fence_after();
-                const uint32_t tS = tmem_base + C::kTmemS + 128u * b;
-                const uint64_t kdesc = kdesc0 + (uint64_t)((rk.idx * C::kKBytes) >> 4);
-                if (elect_one()) {
-                    // D/16 k-steps; k-step ks lives in panel ks/4 at byte offset (ks%4)*32
+            __syncwarp();
+            for (int j = 0; j < nmax; j++) {
+                // ring order K_0 V_0 K_1 V_1 ... (the order the MMA warp releases them in)
 #pragma unroll
-                    for (int ks = 0; ks < D / 16; ks++) {
-                        const uint64_t qoff = (uint64_t)(((ks >> 2) * C::kQPanelBytes + (ks & 3) * 32) >> 4);
-                        const uint64_t koff = (uint64_t)(((ks >> 2) * C::kKPanelBytes + (ks & 3) * 32) >> 4);
-                        if (CG == 1) umma_ss(tS, qdesc + qoff, kdesc + koff, C::kIdescQK, ks > 0 ? 1u : 0u);
-                        else umma_ss_2sm(tS, qdesc + qoff, kdesc + koff, C::kIdescQK, ks > 0 ? 1u : 0u);
-                    }
-                    if (CG == 1) {
-                        umma_commit(bar(C::kBarSFull + b));
-                        umma_commit(bar(C::kBarKEmpty + rk.idx));
-                        if (j == wi.n - 1) umma_commit(bar(C::kBarQEmpty + qslot));   // last reader of this Q tile
-                    } else {
-                        umma_commit_2sm(bar(C::kBarSFull + b));
-                        umma_commit_2sm(bar(C::kBarKEmpty + rk.idx));
-                        if (j == wi.n - 1) umma_commit_2sm(bar(C::kBarQEmpty + qslot));
-                    }
-                }
-                __syncwarp();
-                rk.advance<C::kKStages>();
-                ++gq;
-            }
-        }
-    } else if (warp == kPvWarp && leader) {
-        // =============================== tcgen05.mma issuer: O (+)= P_b V_j ===============================
-        // 8 k-steps of 16 kv rows (P k-step = 8 TMEM columns, V k-step = 16 rows * 128 B), issued in two
-        // halves of 4 k-steps as the two halves of P arrive
-        Ring rv{0u, 0u};
-        uint32_t gp = 0;                                   // global tile index
-        uint32_t nz_units = 0;                             // units with tiles whose PVs have all been issued
-        const uint64_t vdesc0 = umma_smem_desc(sV, C::kVPanelBytes, 1024);
-        const uint32_t tO = tmem_base + C::kTmemO;
-        for (uint32_t it = 0;; ++it) {
-            const int w = next_work(it);
-            if (w < 0) break;
-            const WorkItem wi = decode_work(w, p);
-            for (int j = 0; j < wi.n; j++) {
-                const uint32_t b = gp & 1u, k = gp >> 1;
-                mbar_wait(bar(C::kBarVFull + rv.idx), rv.phase, 13);
-                if (j == 0 && nz_units > 0) mbar_wait(bar(C::kBarOFree), (nz_units - 1u) & 1u, 14);   // epilogue has read O
-                const uint32_t tP = tmem_base + C::kTmemP + 64u * b;
-                const uint64_t vdesc = vdesc0 + (uint64_t)((rv.idx * C::kVBytes) >> 4);
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    mbar_wait(bar(C::kBarPFull + 2 * b + h), k & 1u, 15 + h);
-                    tc_fence_after();
+                for (int kv = 0; kv < 2; kv++) {
+                    const uint32_t full = bar_kv_full + 8 * ring.idx;
+                    mbar_wait(bar_kv_empty + 8 * ring.idx, ring.phase ^ 1u, 2);
                     if (elect_one()) {
+                        mbar_arrive_expect_tx(full, C::kTileBytes);
+                        const uint32_t dst = sKV + ring.idx * C::kTileBytes;
 #pragma unroll
-                        for (int ks = 4 * h; ks < 4 * h + 4; ks++) {
-                            const uint64_t voff = (uint64_t)((ks * 16 * 128) >> 4);
-                            const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-                            if (CG == 1) umma_ts(tO, tP + ks * 8, vdesc + voff, C::kIdescPV, acc);
-                            else umma_ts_2sm(tO, tP + ks * 8, vdesc + voff, C::kIdescPV, acc);
-                        }
-                        if (h == 1) {
-                            if (CG == 1) {
-                                umma_commit(bar(C::kBarPvDone + b));
-                                umma_commit(bar(C::kBarVEmpty + rv.idx));
-                            } else {
-                                umma_commit_2sm(bar(C::kBarPvDone + b));
-                                umma_commit_2sm(bar(C::kBarVEmpty + rv.idx));
-                            }
-                        }
+                        for (int pn = 0; pn < C::kPanels; pn++)
+                            tma_load_3d(dst + pn * C::kPanelBytes, kv == 0 ? &tmK : &tmV, full, pn * 64,
+                                        j * kBlockN, wi.bh);
                     }
                     __syncwarp();
+                    ring.advance<C::kStages>();
                 }
-                rv.advance<C::kVStages>();
-                ++gp;
             }
-            if (wi.n > 0) ++nz_units;
         }
-    } else if (warp == kStoreWarp) {
-        // =============================== O tile store ===============================
-        // Softmax warps stage O_t / l as fp16 in the (now idle) Q buffer of the unit, 128B-swizzled;
-        // this warp hands it to TMA, which clips rows past Nq, and then returns the buffer.
-        for (uint32_t it = 0;; ++it) {
+    } else if (warp == kMmaWarp) {
+        // =============================== tcgen05.mma issuer ===============================
+        Ring rk{0u, 0u};              // ring entry holding K_j
+        Ring rv{1u % C::kStages, 0u}; // ring entry holding V_j
+        uint32_t it = 0;
+        uint32_t p_phase0 = 0u, p_phase1 = 0u;
+        const uint32_t tS0 = tmem_base + C::kTmemS0, tS1 = tmem_base + C::kTmemS1;
+        const uint32_t tO0 = tmem_base + C::kTmemO0, tO1 = tmem_base + C::kTmemO1;
+        const uint64_t qdesc0 = umma_smem_desc(sQ, 16, 1024);
+        const uint64_t qdesc1 = umma_smem_desc(sQ + C::kTileBytes, 16, 1024);
+
+        // S_t = Q_t K_j^T : D/16 k-steps; k-step ks lives in panel ks/4 at byte offset (ks%4)*32
+        auto issue_qk = [&](uint32_t tS, uint64_t qdesc, uint32_t k_smem, uint32_t bar) {
+            const uint64_t kdesc = umma_smem_desc(k_smem, 16, 1024);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ks++) {
+                    const uint64_t off = (uint64_t)(((ks >> 2) * C::kPanelBytes + (ks & 3) * 32) >> 4);
+                    umma_ss(tS, qdesc + off, kdesc + off, C::kIdescQK, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(bar);
+            }
+            __syncwarp();
+        };
+        // O_t (+)= P_t V_j : 8 k-steps of 16 kv rows (P k-step = 8 TMEM columns, V k-step = 16 rows * 128 B),
+        // issued in two halves of 4 k-steps as the two halves of P arrive
+        auto issue_pv = [&](uint32_t tO, uint32_t tP, uint32_t v_smem, bool accumulate, uint32_t bar_p,
+                            uint32_t parity, uint32_t bar_o, int tag) {
+            const uint64_t vdesc = umma_smem_desc(v_smem, C::kPanelBytes, 1024);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                mbar_wait(bar_p + 8 * h, parity, tag);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 4 * h; ks < 4 * h + 4; ks++)
+                        umma_ts(tO, tP + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV,
+                                (accumulate || ks > 0) ? 1u : 0u);
+                    if (h == 1) umma_commit(bar_o);
+                }
+                __syncwarp();
+            }
+        };
+        auto commit = [&](uint32_t bar) {
+            if (elect_one()) umma_commit(bar);
+            __syncwarp();
+        };
+
+        for (;; ++it) {
             const int w = next_work(it);
             if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
-            const uint32_t qslot = it & 1u;
-            const int q_start = wi.q0 + (int)rank * kBlockM;
-            mbar_wait(bar(C::kBarOStaged), it & 1u, 60);
-            const bool do_store = !p.partial_mode && wi.n > 0 && q_start < p.Nq;
-            if (lane == 0) {   // one fixed lane: bulk-group state is per thread
-                if (do_store) {
-#pragma unroll
-                    for (int pn = 0; pn < C::kPanels; pn++)
-                        tma_store_3d(&tmO, sQ + qslot * C::kQTileBytes + pn * C::kQPanelBytes, pn * 64, q_start, wi.bh);
-                    tma_store_commit();
-                    tma_store_wait_read<0>();
-                }
-                mbar_arrive(bar(C::kBarQEmpty + qslot));
+            const int n0 = wi.n0, n1 = wi.n1;
+            const int nmax = n0 > n1 ? n0 : n1;
+            mbar_wait(bar_q_full, it & 1u, 10);
+            tc_fence_after();
+            if (nmax > 0) {
+                mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 11);
+                tc_fence_after();
+                const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
+                if (n0 > 0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
+                if (n1 > 0) issue_qk(tS1, qdesc1, k_smem, bar_s_full + 8);
+                commit(bar_kv_empty + 8 * rk.idx);
+                rk.advance<C::kStages>(); rk.advance<C::kStages>();
             }
-            __syncwarp();
+            // Q is free for the next item as soon as the last QK^T of this one has retired
+            if (nmax <= 1) commit(bar_q_empty);
+            for (int j = 0; j < nmax; j++) {
+                const bool has_next = j + 1 < nmax;
+                mbar_wait(bar_kv_full + 8 * rv.idx, rv.phase, 12);
+                const uint32_t v_smem = sKV + rv.idx * C::kTileBytes;
+                const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
+                // ---- tile 0: PV0(j), QK0(j+1)
+                if (j < n0) {
+                    issue_pv(tO0, tS0, v_smem, j > 0, bar_p_full, p_phase0, bar_o_full, 13);
+                    p_phase0 ^= 1u;
+                }
+                if (has_next) {
+                    mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 15);
+                    tc_fence_after();
+                }
+                if (j + 1 < n0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
+                // ---- tile 1: PV1(j), QK1(j+1)
+                if (j < n1) {
+                    issue_pv(tO1, tS1, v_smem, j > 0, bar_p_full + 16, p_phase1, bar_o_full + 8, 14);
+                    p_phase1 ^= 1u;
+                }
+                commit(bar_kv_empty + 8 * rv.idx);
+                rv.advance<C::kStages>(); rv.advance<C::kStages>();
+                if (j + 1 < n1) issue_qk(tS1, qdesc1, k_smem, bar_s_full + 8);
+                if (has_next) {
+                    commit(bar_kv_empty + 8 * rk.idx);
+                    rk.advance<C::kStages>(); rk.advance<C::kStages>();
+                    if (j + 2 == nmax) commit(bar_q_empty);   // QK^T(nmax-1) was the last reader of Q
+                }
+            }
         }
-        if (lane == 0) tma_store_wait_all<0>();
-        __syncwarp();
     }
     } else {
         setmaxnreg_inc<kRegsSoftmax>();
         // =============================== softmax / correction / epilogue ===============================
-        const int set = warp >> 2;                             // 0: even global tiles, 1: odd
-        const int quad = warp & 3;
-        const int row_in_tile = quad * 32 + lane;              // TMEM lane == S/O row
-        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        SoftmaxCtx c;
-        c.tS = tmem_base + lane_base + C::kTmemS + 128u * set;
-        c.tP = tmem_base + lane_base + C::kTmemP + 64u * set;
-        c.tO = tmem_base + lane_base + C::kTmemO;
-        c.bar_s_free = lbar(C::kBarSFree + set);
-        c.bar_p_full = lbar(C::kBarPFull + 2 * set);
-        c.bar_pv_done_mine = bar(C::kBarPvDone + set);
-        c.bar_pv_done_other = bar(C::kBarPvDone + (set ^ 1));
-        c.bar_m_ready_mine = bar(C::kBarMReady + 4 * set + quad);
-        c.bar_m_ready_other = bar(C::kBarMReady + 4 * (set ^ 1) + quad);
-        c.mref_mine = mref + set * kBlockM + row_in_tile;
-        c.mref_other = mref + (set ^ 1) * kBlockM + row_in_tile;
-        const uint32_t bar_s_full = bar(C::kBarSFull + set);
-        uint32_t g0 = 0;       // global index of the unit's first tile
-        uint32_t nz_units = 0;
+        const int t = warp >> 2;                               // which Q tile of the pair
+        const int row_in_tile = (warp & 3) * 32 + lane;        // TMEM lane == S/O row
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem_base + lane_base + (t ? C::kTmemS1 : C::kTmemS0);
+        const uint32_t tO = tmem_base + lane_base + (t ? C::kTmemO1 : C::kTmemO0);
+        const uint32_t my_s_full = bar_s_full + 8 * t;
+        const uint32_t my_p_full = bar_p_full + 16 * t;        // + 8 * half
+        const uint32_t my_o_full = bar_o_full + 8 * t;
+        uint32_t s_phase = 0;
+        uint32_t pv_count = 0;   // P tiles handed to the MMA warp so far == o_full completions expected
 
         for (uint32_t it = 0;; ++it) {
             const int w = next_work(it);
             if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
-            const int q_start = wi.q0 + (int)rank * kBlockM;
+            const int q_start = wi.q0 + t * kBlockM;
+            if (q_start >= p.Nq) continue;                     // this Q tile does not exist
+            const int n_t = t ? wi.n1 : wi.n0;
             const int row = q_start + row_in_tile;             // local query row
             // keys [0, lim) are visible to this row
             long long lim_ll = p.causal ? (long long)row + p.shift + 1 : (long long)p.Nkv;
@@ -760,166 +553,124 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const int lim = (int)lim_ll;
 
             float m_ref = -INFINITY, l_run = 0.f;
-            for (int j = 0; j < wi.n; j++) {
-                const uint32_t g = g0 + (uint32_t)j;
-                if ((int)(g & 1u) != set) continue;
-                const uint32_t gk = g >> 1;
+            for (int j = 0; j < n_t; j++) {
 #ifdef FA_TIMING
                 const long long tw0 = clock64();
 #endif
-                // Anti-phase: this set starts tile g only after the other set is half-way through tile
-                // g-1 (its m_ready arrival: reference max published, first half of P delivered).  Left
-                // alone the two sets run in lock-step -- both in the MUFU-bound exponential phase at
-                // the same time on the same scheduler, both idle-waiting at the same time -- which
-                // costs ~25 % (profiles/r01_v9d_*).  Half a tile apart, one set's exponentials cover
-                // the other's TMEM loads, row max and barrier round trips.
-#if FA_ANTIPHASE == 1
-                if (g > 0) mbar_wait(c.bar_m_ready_other, ((g - 1u) >> 1) & 1u, 24);
-#endif
-                mbar_wait(bar_s_full, gk & 1u, 20 + set);
+                mbar_wait(my_s_full, s_phase, 20 + t);
+                s_phase ^= 1u;
                 tc_fence_after();
 #ifdef FA_TIMING
                 const long long tw1 = clock64();
 #endif
                 const int k0 = j * kBlockN;
                 const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
-                const uint32_t g_prev_k = (g - 1u) >> 1;       // only used when j > 0
                 if (need_mask)
-                    softmax_tile<D, CG, true>(p, c, lim - k0, j == 0, gk, g_prev_k, m_ref, l_run);
+                    softmax_tile<D, true>(p, tS, tO, my_p_full, my_o_full, lim - k0, j > 0, pv_count, m_ref, l_run);
                 else
-                    softmax_tile<D, CG, false>(p, c, kBlockN, j == 0, gk, g_prev_k, m_ref, l_run);
+                    softmax_tile<D, false>(p, tS, tO, my_p_full, my_o_full, kBlockN, j > 0, pv_count, m_ref, l_run);
+                ++pv_count;
 #ifdef FA_TIMING
-                if (lane == 0 && quad == 0 && j > 1 && (j & 7) < 2) {   // sampled
+                if (lane == 0 && (warp & 3) == 0 && j > 0 && (j & 7) == 0) {   // sampled: 1 tile in 8
                     const long long tw2 = clock64();
-                    atomicAdd(&g_timing[set * 3 + 0], (unsigned long long)(tw1 - tw0));
-                    atomicAdd(&g_timing[set * 3 + 1], (unsigned long long)(tw2 - tw1));
-                    atomicAdd(&g_timing[set * 3 + 2], 1ull);
+                    atomicAdd(&g_timing[t * 3 + 0], (unsigned long long)(tw1 - tw0));
+                    atomicAdd(&g_timing[t * 3 + 1], (unsigned long long)(tw2 - tw1));
+                    atomicAdd(&g_timing[t * 3 + 2], 1ull);
                 }
 #endif
             }
 
-            // ---- epilogue: both sets share it; set s takes O columns [s*D/2, (s+1)*D/2) ----
-            const bool have = wi.n > 0;
-            const bool row_ok = row < p.Nq;
-            const size_t grow = (size_t)wi.bh * p.Nq + (row_ok ? row : 0);
-            constexpr int kHalf = D / 2;
-            const int col0 = set * kHalf;
-            float m_old = -FLT_MAX, l_old = 0.f;
-            if (p.partial_mode && p.accumulate && row_ok) {     // read before set 0 overwrites them below
-                m_old = p.ml[grow * 2 + 0];
-                l_old = p.ml[grow * 2 + 1];
-            }
-            float m_fin = -INFINITY, l_tot = 0.f;
-            if (have) {
-                const uint32_t g_last = g0 + (uint32_t)wi.n - 1u;
-                mbar_wait(bar(C::kBarPvDone + (g_last & 1u)), (g_last >> 1) & 1u, 30 + set);
+            // ---- epilogue: O_t / l -> fp16 -> global (or the partial-state format) ----
+            if (n_t > 0) {
+                mbar_wait(my_o_full, (pv_count - 1u) & 1u, 30 + t);
                 tc_fence_after();
-                // merge the two sets' partial row sums (each relative to the reference max its set last saw)
-                float2* my_fin = fin + ((it & 1u) * 2 + set) * kBlockM + row_in_tile;
-                const float2* ot_fin = fin + ((it & 1u) * 2 + (set ^ 1)) * kBlockM + row_in_tile;
-                reinterpret_cast<volatile float*>(my_fin)[0] = m_ref;
-                reinterpret_cast<volatile float*>(my_fin)[1] = l_run;
-                bar_sync(1, 256);
-                float2 ot;
-                ot.x = reinterpret_cast<const volatile float*>(ot_fin)[0];
-                ot.y = reinterpret_cast<const volatile float*>(ot_fin)[1];
-                m_fin = fmaxf(m_ref, ot.x);
-                const float a_me = (m_ref == -INFINITY) ? 0.f : ex2_approx((m_ref - m_fin) * p.scale_log2);
-                const float a_ot = (ot.x == -INFINITY) ? 0.f : ex2_approx((ot.x - m_fin) * p.scale_log2);
-                l_tot = l_run * a_me + ot.y * a_ot;
             }
-            uint32_t o[kHalf];
-            if (have) {
-#pragma unroll
-                for (int cc = 0; cc < kHalf; cc += 32) tmem_ld_x32(c.tO + col0 + cc, o + cc);
-                tmem_wait_ld();
-                // O is in registers: the first PV of the next unit may overwrite the accumulator
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) arrive_leader<CG>(lbar(C::kBarOFree));
-            } else {
-#pragma unroll
-                for (int i = 0; i < kHalf; i++) o[i] = 0u;
-            }
+            const bool row_ok = row < p.Nq;
+            const size_t grow = (size_t)wi.bh * p.Nq + row;
             if (!p.partial_mode) {
-                const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;   // FA.cu:502-503
-                if (have) {
-                    // fp16 row half -> staging tile (the unit's Q buffer), 16-byte chunks XOR-swizzled by row & 7
-                    const uint32_t stage = sQ + (it & 1u) * C::kQTileBytes;
-                    constexpr int kChunks = kHalf / 8;          // 16-byte chunks this thread writes
+                const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;   // FA.cu:502-503
+                __half* orow = p.o + grow * D;
 #pragma unroll
-                    for (int ch = 0; ch < kChunks; ch++) {
-                        const int col = col0 + ch * 8;          // first of 8 output columns
-                        const int panel = col >> 6;
-                        const int chunk = (col & 63) >> 3;
-                        const uint32_t addr = stage + panel * C::kQPanelBytes + row_in_tile * 128 +
-                                              ((chunk ^ (row_in_tile & 7)) << 4);
-                        const uint32_t* oo = o + ch * 8;
-                        st_shared_v4(addr,
-                                     pack_half2(__uint_as_float(oo[0]) * inv, __uint_as_float(oo[1]) * inv),
-                                     pack_half2(__uint_as_float(oo[2]) * inv, __uint_as_float(oo[3]) * inv),
-                                     pack_half2(__uint_as_float(oo[4]) * inv, __uint_as_float(oo[5]) * inv),
-                                     pack_half2(__uint_as_float(oo[6]) * inv, __uint_as_float(oo[7]) * inv));
+                for (int c = 0; c < D; c += 32) {
+                    uint32_t o[32];
+                    if (n_t > 0) {
+                        tmem_ld_x32(tO + c, o);
+                        tmem_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) o[i] = 0u;
                     }
-                    fence_proxy_async_smem();
-                } else if (row_ok) {
-                    // no key visible to any row of the unit: zeros, straight to global
-                    __half* orow = p.o + grow * D + col0;
+                    if (row_ok) {
 #pragma unroll
-                    for (int i = 0; i < kHalf; i += 8) *reinterpret_cast<uint4*>(orow + i) = make_uint4(0u, 0u, 0u, 0u);
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 v;
+                            __half2 h;
+                            h = __floats2half2_rn(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
+                            v.x = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2half2_rn(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                            v.y = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2half2_rn(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                            v.z = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2half2_rn(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+                            v.w = *reinterpret_cast<uint32_t*>(&h);
+                            *reinterpret_cast<uint4*>(orow + c + i) = v;
+                        }
+                    }
                 }
             } else {
                 // partial state (FA.cu:460-496): un-normalised fp32 O, (m, l) with m in the
                 // scaled-score (natural-log) domain; merge algebra of FA.cu:575-597 when accumulating
-                float m_out = (m_fin == -INFINITY) ? -FLT_MAX : m_fin * p.scale;
-                float l_out = l_tot;
+                float m_out = (m_ref == -INFINITY) ? -FLT_MAX : m_ref * p.scale;
+                float l_out = l_run;
                 float w_new = 1.f, w_old = 0.f;
-                if (p.accumulate) {
+                float* prow = p.o_partial + grow * D;
+                if (p.accumulate && row_ok) {
+                    const float m_old = p.ml[grow * 2 + 0];
+                    const float l_old = p.ml[grow * 2 + 1];
                     const float m_max = fmaxf(m_old, m_out);
                     const float kLog2e = 1.4426950408889634f;
                     w_old = (m_old <= -FLT_MAX) ? 0.f : ex2_approx((m_old - m_max) * kLog2e);
                     w_new = (m_out <= -FLT_MAX) ? 0.f : ex2_approx((m_out - m_max) * kLog2e);
-                    l_out = l_old * w_old + l_tot * w_new;
+                    l_out = l_old * w_old + l_run * w_new;
                     m_out = m_max;
                 }
-                if (row_ok) {
-                    float* prow = p.o_partial + grow * D + col0;
 #pragma unroll
-                    for (int i = 0; i < kHalf; i += 4) {
-                        float4 v = make_float4(__uint_as_float(o[i]) * w_new, __uint_as_float(o[i + 1]) * w_new,
-                                               __uint_as_float(o[i + 2]) * w_new, __uint_as_float(o[i + 3]) * w_new);
-                        if (p.accumulate) {
-                            const float4 old = *reinterpret_cast<const float4*>(prow + i);
-                            v.x += old.x * w_old; v.y += old.y * w_old;
-                            v.z += old.z * w_old; v.w += old.w * w_old;
-                        }
-                        *reinterpret_cast<float4*>(prow + i) = v;
+                for (int c = 0; c < D; c += 32) {
+                    uint32_t o[32];
+                    if (n_t > 0) {
+                        tmem_ld_x32(tO + c, o);
+                        tmem_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) o[i] = 0u;
                     }
-                    if (set == 0) {
-                        // both sets have read the old (m, l) before the fin exchange barrier above when
-                        // the unit has tiles; without tiles nothing changes (w_new = 0 or l = 0)
-                        if (have || !p.accumulate) {
-                            p.ml[grow * 2 + 0] = m_out;
-                            p.ml[grow * 2 + 1] = l_out;
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 v = make_float4(__uint_as_float(o[i]) * w_new, __uint_as_float(o[i + 1]) * w_new,
+                                                   __uint_as_float(o[i + 2]) * w_new, __uint_as_float(o[i + 3]) * w_new);
+                            if (p.accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(prow + c + i);
+                                v.x += old.x * w_old; v.y += old.y * w_old;
+                                v.z += old.z * w_old; v.w += old.w * w_old;
+                            }
+                            *reinterpret_cast<float4*>(prow + c + i) = v;
                         }
                     }
                 }
+                if (row_ok) {
+                    p.ml[grow * 2 + 0] = m_out;
+                    p.ml[grow * 2 + 1] = l_out;
+                }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(C::kBarOStaged));
-            if (have) ++nz_units;
-            g0 += (uint32_t)wi.n;
+            // O_t / S_t are free again: the next item's first P arrival orders after these reads
+            tc_fence_before();
         }
-        (void)nz_units;
     }
 
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (CG == 2) {   // no CTA of the pair may exit while the other can still signal it or read its smem/TMEM
-        cluster_arrive_release();
-        cluster_wait_acquire();
-    }
 #ifdef FA_TIMING
     if (threadIdx.x == 0) {
         unsigned long long t1;
@@ -941,8 +692,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (warp == kMmaWarp) {
         __syncwarp();
         tc_fence_after();
-        if (CG == 1) tmem_dealloc(tmem_base, kTmemCols);
-        else tmem_dealloc_2sm(tmem_base, kTmemCols);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 

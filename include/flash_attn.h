@@ -72,9 +72,10 @@ typedef struct {
     int ctas; /* persistent grid size */
     int tmem_columns;
     int kv_stages; /* K ring entries + V ring entries */
-    int work_items; /* (b, h, q-unit) units the grid loops over; a unit is cta_group Q tiles of 128 rows */
+    int work_items; /* (b, h, q-unit) items the grid loops over: 256 query rows each for the default kernel */
     int num_sms;
-    int cta_group; /* CTAs cooperating on one unit: 2 = tcgen05.mma.cta_group::2 pairs (D = 128), 1 otherwise */
+    int cta_group; /* CTAs cooperating on one item: 1 (default kernel); 2 = tcgen05.mma.cta_group::2 pairs of the
+                      experimental kernel selected with FLASH_ATTN_B200_KERNEL=pair */
 } flash_attn_kernel_info;
 int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_attn_kernel_info* info);
 

@@ -1,6 +1,6 @@
 """Bring-up diagnostics for the sm_100a kernel (run on the GPU box).
 
-  python tests/harness/diagnose.py [group ...]     groups: basic structured full
+  python tests/harness/diagnose.py [group ...]     groups: basic structured full sharp
 Prints one line per case (max-abs / mean-abs vs the CPU oracle) and, on failure, where the
 error lives (row blocks / column blocks), which is what identifies a descriptor or layout bug.
 """
@@ -111,6 +111,25 @@ def group_structured():
     return ok
 
 
+def group_sharp():
+    """Row maxima that keep jumping by far more than the lazy-rescale threshold (2^8): every path of
+    the shared-reference protocol (raise, other set raised meanwhile, both) runs many times."""
+    ok = True
+    for (B, H, N, D, causal, ramp) in [(1, 2, 1024, 128, 0, 6.0), (1, 2, 1024, 128, 1, 6.0), (1, 3, 2048, 128, 1, 12.0),
+                                       (1, 2, 1000, 128, 0, 8.0), (2, 2, 1024, 64, 1, 6.0), (1, 2, 4096, 128, 0, 3.0)]:
+        rng = np.random.default_rng(N + int(ramp))
+        q = (rng.standard_normal((B, H, N, D), dtype=np.float32) * 2.0).astype(np.float16)
+        k = rng.standard_normal((B, H, N, D), dtype=np.float32)
+        k *= (1.0 + ramp * np.arange(N, dtype=np.float32) / N)[None, None, :, None]      # later keys score higher
+        k[:, :, ::97, :] *= 3.0                                                           # and isolated spikes
+        k = k.astype(np.float16)
+        v = rng.standard_normal((B, H, N, D), dtype=np.float32).astype(np.float16)
+        ref = _oracle.attention(q, k, v, causal)
+        out = run_gpu(q, k, v, causal)
+        ok &= report(f"sharp ramp={ramp} B{B} H{H} N{N} D{D} causal={causal}", out, ref)
+    return ok
+
+
 def group_full():
     ok = True
     # the reference's own four checks (FA.cu:757-884), its input stream, gated at 2e-3 / 2e-4
@@ -142,7 +161,7 @@ if __name__ == "__main__":
     for g in groups:
         print(f"== {g} ==", flush=True)
         try:
-            allok &= {"basic": group_basic, "structured": group_structured, "full": group_full}[g]()
+            allok &= {"basic": group_basic, "structured": group_structured, "full": group_full, "sharp": group_sharp}[g]()
         except Exception as e:  # a trapped kernel poisons the context: stop this process
             print(f"EXCEPTION in group {g}: {type(e).__name__}: {e}", flush=True)
             allok = False

@@ -1,4 +1,4 @@
-"""CPU-only: the persistent kernel's work decomposition (a work item = one head x cta_group 128-row Q tiles) (host mirror of fa::decode_work, which
+"""CPU-only: the persistent kernel's work decomposition (a work item = one head x tiles_per_item 128-row Q tiles) (host mirror of fa::decode_work, which
 replaces the reference's blockIdx mapping / GRID_SWAP, flash_attention.cu:103-112): every
 (head, q-tile) exactly once, heavy-first inside a head, fully masked KV tiles skipped."""
 import pytest
@@ -22,7 +22,7 @@ def test_every_q_tile_exactly_once(N, causal):
     B, H = 2, 3
     its = items(B, H, N, N, 128, causal)
     nq_tiles = (N + 127) // 128
-    cg = fa.cta_group(128)
+    cg = fa.tiles_per_item(128)
     seen = set()
     for it in its:
         if cg == 1:
@@ -44,7 +44,7 @@ def test_every_q_tile_exactly_once(N, causal):
 def test_heavy_first_within_l2_sized_head_groups():
     # N=8192 D=128: K+V of a head = 4 MB -> 16 heads per group; inside a group heavy-first across heads
     its = items(1, 32, 8192, 8192, 128, True)
-    nqp = 64 // fa.cta_group(128)
+    nqp = 64 // fa.tiles_per_item(128)
     per_group = 16 * nqp
     assert len(its) == 32 * nqp
     for g in range(2):
@@ -67,7 +67,7 @@ def test_last_group_may_be_smaller():
     # 5 heads of 16 MB K/V each (N=32768): groups of 4 + 1, every (head, pair) still exactly once
     its = items(1, 5, 32768, 32768, 128, True)
     seen = {(it["bh"], it["q0"]) for it in its}
-    units = 256 // fa.cta_group(128)
+    units = 256 // fa.tiles_per_item(128)
     assert len(seen) == len(its) == 5 * units
     assert [it["bh"] for it in its[:4]] == [0, 1, 2, 3] and its[4 * units]["bh"] == 4
 
