@@ -414,7 +414,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": round(e2e_val, 3), "unit": "TFLOPS", "h2d_bytes_per_step": 3 * nbytes,
                 "d2h_bytes_per_step": nbytes, "ms_per_step": round(e2e_ms, 4), "steps": e2e_steps,
-                "call": "flash_attn_fwd_host (pinned host Q,K,V -> device, kernel, O -> pinned host)"
+                "call": "flash_attn_fwd_host (pinned host Q,K,V -> device, kernel, O -> pinned host; 8 head chunks "
+                        "pipelined over three streams, every byte still crosses PCIe inside the timed region)"
                         if args.impl == "ours" else "H2D x3 + flash_attention_v9_dispatch + D2H (FA.cu:774-780)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": round(tflops_rank, 2), "peak": pk["tflops"], "unit": "TFLOP/s",

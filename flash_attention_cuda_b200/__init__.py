@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = (
     "flash_attn_finalize",
     "flash_attn_fwd_host",
     "flash_attn_get_kernel_info",
+    "flash_attn_set_sm_margin",
     "flash_attn_launch_count",
     "flash_attn_destroy",
     "flash_attn_error_string",
@@ -95,6 +96,9 @@ def lib() -> ctypes.CDLL:
     L.flash_attn_fwd_host.restype = ci
     L.flash_attn_get_kernel_info.argtypes = [ci, ci, ci, ci, ci, ctypes.POINTER(KernelInfo)]
     L.flash_attn_get_kernel_info.restype = ci
+    if hasattr(L, "flash_attn_set_sm_margin"):   # absent from archived A/B builds of older kernels
+        L.flash_attn_set_sm_margin.argtypes = [ci]
+        L.flash_attn_set_sm_margin.restype = ci
     L.flash_attn_launch_count.argtypes = []
     L.flash_attn_launch_count.restype = ctypes.c_ulonglong
     L.flash_attn_destroy.argtypes = []
@@ -183,6 +187,11 @@ def watchdog_status() -> dict:
     buf = (ctypes.c_uint * 4)()
     check(lib().flash_attn_debug_status(buf))
     return {"aborted": int(buf[0]), "tag": int(buf[1]), "block": int(buf[2]), "thread": int(buf[3])}
+
+
+def set_sm_margin(sms: int) -> int:
+    """Leave `sms` SMs free in every later launch (room for NCCL kernels); returns the previous value."""
+    return int(lib().flash_attn_set_sm_margin(int(sms)))
 
 
 def launch_count() -> int:

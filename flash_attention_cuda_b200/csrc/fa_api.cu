@@ -19,6 +19,7 @@ namespace {
 
 constexpr int kMaxDevices = 64;
 constexpr int kSchedSlots = 4096;
+constexpr int kHostChunks = 8;     // head chunks flash_attn_fwd_host pipelines over PCIe
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -26,6 +27,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapFloatOOBfill);
 
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_sm_margin{0};     // SMs the persistent grid leaves free (flash_attn_set_sm_margin)
 std::once_flag g_encode_once;
 EncodeTiledFn g_encode = nullptr;
 
@@ -42,7 +44,10 @@ struct DeviceState {
     std::mutex host_mu;
     void* stage = nullptr;
     size_t stage_bytes = 0;
-    cudaStream_t host_stream = nullptr;
+    // three streams (H2D, kernels, D2H) and per-chunk events: the host entry point pipelines head chunks
+    cudaStream_t host_stream = nullptr, host_in = nullptr, host_out = nullptr;
+    cudaEvent_t ev_in[kHostChunks] = {}, ev_k[kHostChunks] = {};
+    bool host_ready = false;
 };
 DeviceState g_dev[kMaxDevices];
 
@@ -164,7 +169,9 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
 template <int D>
 int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
            fa::Params p, cudaStream_t stream) {
-    int grid = p.total_work < st->num_sms ? p.total_work : st->num_sms;
+    int avail = st->num_sms - g_sm_margin.load(std::memory_order_relaxed);
+    if (avail < 1) avail = 1;
+    int grid = p.total_work < avail ? p.total_work : avail;
     if (grid < 1) grid = 1;
     p.sched = st->sched + 2 * (st->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
     // launched with programmatic stream serialization (PDL): the kernel's prologue overlaps the tail
@@ -205,7 +212,9 @@ fa_pair::Params make_pair_params(const fa::Params& b, int D) {
 template <int D, int CG>
 int launch_pair(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                 const CUtensorMap& to, fa_pair::Params p, cudaStream_t stream) {
-    int units = p.total_work < st->num_sms / CG ? p.total_work : st->num_sms / CG;
+    int avail = (st->num_sms - g_sm_margin.load(std::memory_order_relaxed)) / CG;
+    if (avail < 1) avail = 1;
+    int units = p.total_work < avail ? p.total_work : avail;
     if (units < 1) units = 1;
     p.sched = st->sched + 2 * (st->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
     cudaLaunchConfig_t cfg;
@@ -311,8 +320,15 @@ int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho
     const size_t bytes = (size_t)B * H * N * D * sizeof(__half);
     std::lock_guard<std::mutex> lock(st->host_mu);
     cudaError_t e;
-    if (!st->host_stream) {
+    if (!st->host_ready) {
         if ((e = cudaStreamCreateWithFlags(&st->host_stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamCreateWithFlags(&st->host_in, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamCreateWithFlags(&st->host_out, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        for (int i = 0; i < kHostChunks; i++) {
+            if ((e = cudaEventCreateWithFlags(&st->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+            if ((e = cudaEventCreateWithFlags(&st->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+        }
+        st->host_ready = true;
     }
     if (st->stage_bytes < 4 * bytes) {
         if (st->stage) cudaFree(st->stage);
@@ -322,17 +338,36 @@ int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho
         st->stage_bytes = 4 * bytes;
     }
     char* base = static_cast<char*>(st->stage);
-    void *dq = base, *dk = base + bytes, *dv = base + 2 * bytes, *dout = base + 3 * bytes;
-    cudaStream_t s = st->host_stream;
-    // FA.cu:774-776
-    if ((e = cudaMemcpyAsync(dq, hq, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemcpyAsync(dk, hk, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemcpyAsync(dv, hv, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
-    int rc = flash_attn_fwd(dq, dk, dv, dout, B, H, N, D, causal, s);   // FA.cu:777
-    if (rc != FA_OK) return rc;
-    // FA.cu:779-780
-    if ((e = cudaMemcpyAsync(ho, dout, bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
-    return (int)cudaStreamSynchronize(s);
+    char *dq = base, *dk = base + bytes, *dv = base + 2 * bytes, *dout = base + 3 * bytes;
+    // The reference copies everything in, dispatches, copies everything out (FA.cu:774-780).  Heads are
+    // independent, so the same work is cut into head chunks and pipelined: while chunk c computes,
+    // chunk c+1 is on its way in and chunk c-1 on its way out (PCIe is full duplex; three streams,
+    // one event pair per chunk).  The wire time of Q, K, V dominates; kernels and O hide under it.
+    const int BH = B * H;
+    const int chunks = BH < kHostChunks ? BH : kHostChunks;
+    const size_t head_bytes = (size_t)N * D * sizeof(__half);
+    int h0 = 0;
+    for (int c = 0; c < chunks; c++) {
+        const int h1 = (int)((long long)BH * (c + 1) / chunks);
+        const int nh = h1 - h0;
+        const size_t off = (size_t)h0 * head_bytes, len = (size_t)nh * head_bytes;
+        const char *hq8 = static_cast<const char*>(hq), *hk8 = static_cast<const char*>(hk),
+                   *hv8 = static_cast<const char*>(hv);
+        if ((e = cudaMemcpyAsync(dq + off, hq8 + off, len, cudaMemcpyHostToDevice, st->host_in)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(dk + off, hk8 + off, len, cudaMemcpyHostToDevice, st->host_in)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(dv + off, hv8 + off, len, cudaMemcpyHostToDevice, st->host_in)) != cudaSuccess) return (int)e;
+        if ((e = cudaEventRecord(st->ev_in[c], st->host_in)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamWaitEvent(st->host_stream, st->ev_in[c], 0)) != cudaSuccess) return (int)e;
+        int rc = flash_attn_fwd(dq + off, dk + off, dv + off, dout + off, 1, nh, N, D, causal, st->host_stream);   // FA.cu:777
+        if (rc != FA_OK) return rc;
+        if ((e = cudaEventRecord(st->ev_k[c], st->host_stream)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamWaitEvent(st->host_out, st->ev_k[c], 0)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(static_cast<char*>(ho) + off, dout + off, len, cudaMemcpyDeviceToHost, st->host_out)) !=
+            cudaSuccess)
+            return (int)e;
+        h0 = h1;
+    }
+    return (int)cudaStreamSynchronize(st->host_out);
 }
 
 int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_attn_kernel_info* info) {
@@ -388,6 +423,11 @@ int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_att
     return FA_OK;
 }
 
+int flash_attn_set_sm_margin(int sms) {
+    if (sms < 0) sms = 0;
+    return g_sm_margin.exchange(sms, std::memory_order_relaxed);
+}
+
 unsigned long long flash_attn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void flash_attn_destroy(void) {
@@ -396,13 +436,21 @@ void flash_attn_destroy(void) {
     for (int d = 0; d < kMaxDevices; d++) {
         DeviceState* st = &g_dev[d];
         std::lock_guard<std::mutex> lock(st->host_mu);
-        if (st->stage || st->host_stream) {
+        if (st->stage || st->host_ready) {
             cudaSetDevice(d);
             if (st->stage) cudaFree(st->stage);
             if (st->host_stream) cudaStreamDestroy(st->host_stream);
+            if (st->host_in) cudaStreamDestroy(st->host_in);
+            if (st->host_out) cudaStreamDestroy(st->host_out);
+            for (int i = 0; i < kHostChunks; i++) {
+                if (st->ev_in[i]) cudaEventDestroy(st->ev_in[i]);
+                if (st->ev_k[i]) cudaEventDestroy(st->ev_k[i]);
+                st->ev_in[i] = st->ev_k[i] = nullptr;
+            }
             st->stage = nullptr;
             st->stage_bytes = 0;
-            st->host_stream = nullptr;
+            st->host_stream = st->host_in = st->host_out = nullptr;
+            st->host_ready = false;
         }
     }
     cudaSetDevice(saved);

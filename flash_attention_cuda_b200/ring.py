@@ -47,6 +47,10 @@ def hop_pairs(rank: int, src: int, world: int, causal: bool) -> List[Tuple[int, 
     return out
 
 
+# SMs left to NCCL while a ring is running (see flash_attn_set_sm_margin); FLASH_ATTN_RING_SM_MARGIN overrides
+DEFAULT_RING_SM_MARGIN = 16
+
+
 def _cuda_partial(q, k, v, o_partial, ml, causal, q_offset, kv_offset, accumulate):
     from . import flash_attn_fwd_partial
     flash_attn_fwd_partial(q, k, v, o_partial, ml, causal, q_offset, kv_offset, accumulate)
@@ -86,6 +90,11 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
     recv_from = (rank - 1) % world
     if on_cuda and comm_stream is None and world > 1:
         comm_stream = torch.cuda.Stream(device=dev)
+    old_margin = None
+    if on_cuda and world > 1 and partial is _cuda_partial:
+        import os
+        from . import set_sm_margin
+        old_margin = set_sm_margin(int(os.environ.get("FLASH_ATTN_RING_SM_MARGIN", DEFAULT_RING_SM_MARGIN)))
 
     qa = zigzag_chunks(rank, world)
     for hop in range(world):
@@ -114,6 +123,9 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
                 torch.cuda.current_stream(dev).wait_stream(comm_stream)
                 comm_stream.wait_stream(torch.cuda.current_stream(dev))   # kernels that read cur are ordered first
             cur, nxt = nxt, cur
+    if old_margin is not None:
+        from . import set_sm_margin
+        set_sm_margin(old_margin)
     out = [torch.empty_like(q[0]), torch.empty_like(q[1])]
     for i in range(2):
         finalize(o_part[i], ml[i], out[i])

@@ -79,6 +79,13 @@ typedef struct {
 } flash_attn_kernel_info;
 int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_attn_kernel_info* info);
 
+/* The kernel is persistent: one CTA per SM, all of the SM's shared memory.  A communication kernel
+ * (NCCL send/recv of the next K/V block in ring context parallelism) cannot become resident next to
+ * it, so its transfer would serialise behind the attention kernel instead of overlapping it.
+ * `sms` > 0 makes every later launch of this process leave that many SMs free.  Returns the
+ * previous value; 0 (default) uses the whole device. */
+int flash_attn_set_sm_margin(int sms);
+
 /* Number of kernels this library has launched in the calling process (all threads). */
 unsigned long long flash_attn_launch_count(void);
 
