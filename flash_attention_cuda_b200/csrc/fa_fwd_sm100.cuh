@@ -46,7 +46,6 @@ constexpr int kBlockM = 128;      // Q rows per tile  (UMMA M)
 constexpr int kBlockN = 128;      // K/V rows per tile (UMMA N of QK^T, K extent of PV)
 constexpr int kNumThreads = 384;
 constexpr int kMmaWarp = 8;
-constexpr int kMmaWarp2 = 10;     // FA_TWO_ISSUERS: issuer of Q tile 1's MMAs (otherwise an idle pad warp)
 constexpr int kLoadWarp = 9;
 constexpr int kTmemCols = 512;
 constexpr int kRegsSoftmax = 208;   // setmaxnreg: softmax warpgroups grow, the producer/MMA warpgroup shrinks
@@ -55,12 +54,6 @@ constexpr float kRescaleThreshold = 8.0f;
 // Of every 4 element pairs, this many take exp2 on the FMA pipe (Cody-Waite + degree-3 minimax)
 // instead of MUFU.EX2: at 16 MUFU/clk/SM the 16384 exponentials of a 128x128 tile cost as many
 // cycles as its two MMAs, so the SFU -- not the tensor core -- would set the pace.
-// One tcgen05.mma issuer warp per Q tile instead of one for both.  Only PV_t(j) -> QK_t(j+1) must stay
-// in one thread's (in-order) stream; the two tiles' chains are independent, and a lone warp needs
-// ~6 cycles per dependent instruction, so a shared issuer adds its own queueing to both chains.
-#ifndef FA_TWO_ISSUERS
-#define FA_TWO_ISSUERS 0
-#endif
 #ifndef FA_POLY_PAIRS
 #define FA_POLY_PAIRS 1
 #endif
@@ -327,10 +320,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
     if (threadIdx.x == 0) {
         mbar_init(bar_q_full, 1);
-        mbar_init(bar_q_empty, FA_TWO_ISSUERS ? 2 : 1);
+        mbar_init(bar_q_empty, 1);
         for (int i = 0; i < C::kStages; i++) {
             mbar_init(bar_kv_full + 8 * i, 1);
-            mbar_init(bar_kv_empty + 8 * i, FA_TWO_ISSUERS ? 2 : 1);
+            mbar_init(bar_kv_empty + 8 * i, 1);
         }
         for (int t = 0; t < 2; t++) {
             mbar_init(bar_s_full + 8 * t, 1);
@@ -340,7 +333,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_sched_full + 8 * i, 1);
-            mbar_init(bar_sched_empty + 8 * i, FA_TWO_ISSUERS ? 10 : 9);    // MMA warp(s) + 8 softmax warps
+            mbar_init(bar_sched_empty + 8 * i, 9);    // MMA warp + 8 softmax warps
         }
         fence_mbar_init();
     }
@@ -433,85 +426,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 }
             }
         }
-#if FA_TWO_ISSUERS
-    } else if (warp == kMmaWarp || warp == kMmaWarp2) {
-        // =============================== tcgen05.mma issuer of Q tile t ===============================
-        const int t = (warp == kMmaWarp) ? 0 : 1;
-        Ring rk{0u, 0u};              // ring entry holding K_j
-        Ring rv{1u % C::kStages, 0u}; // ring entry holding V_j
-        uint32_t p_phase = 0u;
-        const uint32_t tS = tmem_base + (t ? C::kTmemS1 : C::kTmemS0);
-        const uint32_t tO = tmem_base + (t ? C::kTmemO1 : C::kTmemO0);
-        const uint64_t qdesc = umma_smem_desc(sQ + t * C::kTileBytes, 16, 1024);
-        const uint32_t my_s_full = bar_s_full + 8 * t, my_p_full = bar_p_full + 16 * t, my_o_full = bar_o_full + 8 * t;
-        // ring entries and Q are released by both issuers (barrier count 2); an issuer whose tile needs
-        // fewer KV tiles than the other still walks the ring and commits
-        auto release = [&](uint32_t bar) {
-            if (elect_one()) umma_commit(bar);
-            __syncwarp();
-        };
-        auto qk = [&](uint32_t k_smem) {
-            const uint64_t kdesc = umma_smem_desc(k_smem, 16, 1024);
-            if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < D / 16; ks++) {
-                    const uint64_t off = (uint64_t)(((ks >> 2) * C::kPanelBytes + (ks & 3) * 32) >> 4);
-                    umma_ss(tS, qdesc + off, kdesc + off, C::kIdescQK, ks > 0 ? 1u : 0u);
-                }
-                umma_commit(my_s_full);
-            }
-            __syncwarp();
-        };
-        for (uint32_t it = 0;; ++it) {
-            const int w = next_work(it);
-            if (w < 0) break;
-            const WorkItem wi = decode_work(w, p);
-            const int n_t = t ? wi.n1 : wi.n0;
-            const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
-            mbar_wait(bar_q_full, it & 1u, 10);
-            tc_fence_after();
-            if (nmax > 0) {
-                mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 11);
-                tc_fence_after();
-                if (n_t > 0) qk(sKV + rk.idx * C::kTileBytes);
-                release(bar_kv_empty + 8 * rk.idx);
-                rk.advance<C::kStages>(); rk.advance<C::kStages>();
-            }
-            if (nmax <= 1) release(bar_q_empty);
-            for (int j = 0; j < nmax; j++) {
-                const bool has_next = j + 1 < nmax;
-                mbar_wait(bar_kv_full + 8 * rv.idx, rv.phase, 12);
-                if (j < n_t) {
-                    // O_t (+)= P_t V_j in two halves of 4 k-steps as the two halves of P arrive
-                    const uint64_t vdesc = umma_smem_desc(sKV + rv.idx * C::kTileBytes, C::kPanelBytes, 1024);
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        mbar_wait(my_p_full + 8 * h, p_phase, 13 + t);
-                        tc_fence_after();
-                        if (elect_one()) {
-#pragma unroll
-                            for (int ks = 4 * h; ks < 4 * h + 4; ks++)
-                                umma_ts(tO, tS + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV,
-                                        (j > 0 || ks > 0) ? 1u : 0u);
-                            if (h == 1) umma_commit(my_o_full);
-                        }
-                        __syncwarp();
-                    }
-                    p_phase ^= 1u;
-                }
-                release(bar_kv_empty + 8 * rv.idx);
-                rv.advance<C::kStages>(); rv.advance<C::kStages>();
-                if (has_next) {
-                    mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 15);
-                    tc_fence_after();
-                    if (j + 1 < n_t) qk(sKV + rk.idx * C::kTileBytes);
-                    release(bar_kv_empty + 8 * rk.idx);
-                    rk.advance<C::kStages>(); rk.advance<C::kStages>();
-                    if (j + 2 == nmax) release(bar_q_empty);   // QK^T(nmax-1) was the last reader of Q
-                }
-            }
-        }
-#else
     } else if (warp == kMmaWarp) {
         // =============================== tcgen05.mma issuer ===============================
         Ring rk{0u, 0u};              // ring entry holding K_j
@@ -609,7 +523,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 }
             }
         }
-#endif
     }
     } else {
         setmaxnreg_inc<kRegsSoftmax>();

@@ -51,6 +51,9 @@ def hop_pairs(rank: int, src: int, world: int, causal: bool) -> List[Tuple[int, 
 DEFAULT_RING_SM_MARGIN = 16
 
 
+_workspace: dict = {}     # see ring_attention_forward
+
+
 def _cuda_partial(q, k, v, o_partial, ml, causal, q_offset, kv_offset, accumulate):
     from . import flash_attn_fwd_partial
     flash_attn_fwd_partial(q, k, v, o_partial, ml, causal, q_offset, kv_offset, accumulate)
@@ -80,12 +83,24 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
     dev = q[0].device
     on_cuda = dev.type == "cuda"
 
-    o_part = [torch.zeros((B * H * C, D), dtype=torch.float32, device=dev) for _ in range(2)]
-    ml = [torch.zeros((B * H * C, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+    # partial state and receive buffers are cached per (device, shape): a ring step allocates nothing.
+    # No zero-fill either: the first chunk pair of a Q chunk runs with accumulate = False and overwrites.
+    key = (str(dev), B, H, C, D, q[0].dtype, world > 1)
+    ws = _workspace.get(key)
+    if ws is None:
+        ws = {
+            "o_part": [torch.empty((B * H * C, D), dtype=torch.float32, device=dev) for _ in range(2)],
+            "ml": [torch.empty((B * H * C, 2), dtype=torch.float32, device=dev) for _ in range(2)],
+            "recv": [[torch.empty_like(k[0]) for _ in range(4)] for _ in range(2)] if world > 1 else None,
+        }
+        _workspace.clear()          # one shape at a time: the buffers are large
+        _workspace[key] = ws
+    o_part, ml = ws["o_part"], ws["ml"]
     started = [False, False]
 
     cur = [k[0], k[1], v[0], v[1]]
-    nxt = [torch.empty_like(t) for t in cur] if world > 1 else None
+    # two receive sets: hop h receives into set h & 1 while set (h - 1) & 1 (or the caller's k, v) is read
+    nxt = ws["recv"][0] if world > 1 else None
     send_to = (rank + 1) % world
     recv_from = (rank - 1) % world
     if on_cuda and comm_stream is None and world > 1:
@@ -122,7 +137,7 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
             if on_cuda:
                 torch.cuda.current_stream(dev).wait_stream(comm_stream)
                 comm_stream.wait_stream(torch.cuda.current_stream(dev))   # kernels that read cur are ordered first
-            cur, nxt = nxt, cur
+            cur, nxt = nxt, ws["recv"][(hop + 1) & 1]
     if old_margin is not None:
         from . import set_sm_margin
         set_sm_margin(old_margin)
