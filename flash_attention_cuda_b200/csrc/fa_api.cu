@@ -168,7 +168,7 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
 
 template <int D>
 int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-           fa::Params p, cudaStream_t stream) {
+           const CUtensorMap& to, fa::Params p, cudaStream_t stream) {
     int avail = st->num_sms - g_sm_margin.load(std::memory_order_relaxed);
     if (avail < 1) avail = 1;
     int grid = p.total_work < avail ? p.total_work : avail;
@@ -187,7 +187,7 @@ int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D>, tq, tk, tv, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D>, tq, tk, tv, to, p);
     if (le != cudaSuccess) return (int)le;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();   // FA.cu:662
@@ -260,12 +260,14 @@ int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaS
     if (!st) return err;
     if (use_pair_kernel()) return run_pair(st, q, k, v, p, D, stream);
     if ((long long)p.BH * p.nqp > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
-    CUtensorMap tq, tk, tv;
+    CUtensorMap tq, tk, tv, to;
     int rc;
     if ((rc = make_tmap(&tq, q, p.BH, p.Nq, D)) != FA_OK) return rc;
     if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D)) != FA_OK) return rc;
     if ((rc = make_tmap(&tv, v, p.BH, p.Nkv, D)) != FA_OK) return rc;
-    return D == 128 ? launch<128>(st, tq, tk, tv, p, stream) : launch<64>(st, tq, tk, tv, p, stream);
+    // O store map (unused in partial mode: describe Q's extent on a valid pointer)
+    if ((rc = make_tmap(&to, p.o ? (const void*)p.o : q, p.BH, p.Nq, D)) != FA_OK) return rc;
+    return D == 128 ? launch<128>(st, tq, tk, tv, to, p, stream) : launch<64>(st, tq, tk, tv, to, p, stream);
 }
 
 }  // namespace

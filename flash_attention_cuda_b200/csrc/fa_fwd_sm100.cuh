@@ -3,20 +3,27 @@
 //
 // Replaces the reference's device path flash_attention_v9<...> (flash_attention.cu:67-554):
 //   FA.cu:103-112  block->(bh, q-block) mapping, GRID_SWAP    -> persistent work loop, heavy-first
-//   FA.cu:145-159  Q fragments in registers                   -> Q tile pair resident in smem (TMA)
-//   FA.cu:417-447  synchronous K/V tile load + 2 barriers     -> producer warp, mbarrier ring
+//   FA.cu:145-159  Q fragments in registers                   -> Q tile pair resident in smem (TMA), two slots
+//   FA.cu:417-447  synchronous K/V tile load + 2 barriers     -> producer warp, 3-entry mbarrier ring
 //   FA.cu:188-233  DO_QK_MATMUL (mma.sync m16n8k16)           -> tcgen05.mma SS, S in TMEM
 //   FA.cu:235-288  DO_SOFTMAX (quad shuffles, eager rescale)  -> one thread per row, lazy rescale
 //   FA.cu:290-334  DO_PV_MATMUL (P in registers)              -> P fp16 in TMEM, tcgen05.mma TS
-//   FA.cu:497-553  epilogue via smem                          -> TMEM -> registers -> global
+//   FA.cu:497-553  multi-pass smem output staging             -> TMEM -> registers -> swizzled smem -> TMA store
 //   FA.cu:460-496  split-K partial epilogue (dead code there) -> partial mode used by ring CP
 //
 // CTA = 384 threads:  warps 0-3  softmax/correction/epilogue for Q tile 0 (128 rows)
 //                     warps 4-7  same for Q tile 1
 //                     warp 8     TMEM allocator + tcgen05.mma issuer (one lane)
 //                     warp 9     TMA producer (one lane)
-//                     warps 10,11 idle (pad the third warpgroup)
+//                     warp 10    TMA store of finished O tiles
+//                     warp 11    idle (pads the third warpgroup)
 // One CTA per SM; each CTA loops over work items (bh, pair of 128-row Q tiles).
+//
+// Shared memory (D=128): Q 2 slots x 2 tiles x 32 KB, K/V ring 3 x 32 KB.  Items alternate between the
+// Q slots: the next item's Q pair is loaded while the current one runs, and its first QK^T is issued
+// right behind the current item's last PV (the softmax warps are then still in the epilogue), so the
+// tensor pipe does not drain at item boundaries -- worth 2 % at N=8192, 10-19 % at N<=1024.  After its
+// last QK^T a slot stages the item's O tiles (fp16, 128B-swizzled) for the TMA store.
 //
 // TMEM (512 columns x 128 lanes x 32 bit): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).
 // P_t (fp16, two per column) overwrites columns [0,64) of S_t once the owning thread has read
@@ -47,6 +54,7 @@ constexpr int kBlockN = 128;      // K/V rows per tile (UMMA N of QK^T, K extent
 constexpr int kNumThreads = 384;
 constexpr int kMmaWarp = 8;
 constexpr int kLoadWarp = 9;
+constexpr int kStoreWarp = 10;
 constexpr int kTmemCols = 512;
 constexpr int kRegsSoftmax = 208;   // setmaxnreg: softmax warpgroups grow, the producer/MMA warpgroup shrinks
 constexpr int kRegsOther = 80;      // 2*128*208 + 128*80 = 63488 <= 168 (launch) * 384
@@ -65,12 +73,18 @@ struct Cfg {
     static constexpr int kPanels = D / 64;                 // 128-byte swizzle panels per row
     static constexpr int kPanelBytes = 128 * 128;          // 128 rows x 128 B
     static constexpr int kTileBytes = kPanels * kPanelBytes;
-    static constexpr int kStages = (D == 128) ? 5 : 8;     // K/V ring entries (one tile each)
-    static constexpr int kSmemQ = 2 * kTileBytes;
+    // K/V ring entries (one tile each).  Depth 3, 4 and 5 measure the same (profiles/r01_v4b_*): the
+    // ring only has to cover one TMA round trip, so the shared memory goes to a second Q buffer instead.
+    static constexpr int kStages = (D == 128) ? 3 : 8;
+    // Q: two slots (work items alternate) x two tiles.  While item i runs, item i+1's Q pair is already
+    // resident, so its first QK^T goes out right behind item i's last PV; after item i's last QK^T its
+    // slot doubles as the staging buffer of its O tiles until the TMA store has read them.
+    static constexpr int kSmemQ = 4 * kTileBytes;
     static constexpr int kSmemKV = kStages * kTileBytes;
     static constexpr int kBarOffset = kSmemQ + kSmemKV;
-    static constexpr int kNumBars = 2 + 2 * kStages + 8 + 4;
+    static constexpr int kNumBars = 4 + 2 * kStages + 8 + 2 + 4;
     static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 32 + 1024;  // +32: tmem slot, scheduler slots; +1024: manual alignment slack
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
     static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
     static constexpr uint32_t kIdescQK = umma_idesc_f16(kBlockM, kBlockN, 0, 0);
     static constexpr uint32_t kIdescPV = umma_idesc_f16(kBlockM, D, 0, 1);  // V is MN-major ([kv][d], d contiguous)
@@ -286,7 +300,7 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
 template <int D>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-              const __grid_constant__ CUtensorMap tmV, const Params p) {
+              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
     using C = Cfg<D>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -294,14 +308,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t sQ = smem_base;
     const uint32_t sKV = smem_base + C::kSmemQ;
     const uint32_t bars = smem_base + C::kBarOffset;
-    const uint32_t bar_q_full = bars + 0;
-    const uint32_t bar_q_empty = bars + 8;
-    const uint32_t bar_kv_full = bars + 16;                       // [kStages]
+    const uint32_t bar_q_full = bars + 0;                         // [slot]
+    const uint32_t bar_q_empty = bars + 16;                       // [slot]
+    const uint32_t bar_kv_full = bars + 32;                       // [kStages]
     const uint32_t bar_kv_empty = bar_kv_full + 8 * C::kStages;   // [kStages]
     const uint32_t bar_s_full = bar_kv_empty + 8 * C::kStages;    // [tile]
     const uint32_t bar_p_full = bar_s_full + 16;                  // [tile][half]  index 2*t + h
     const uint32_t bar_o_full = bar_p_full + 32;                  // [tile]
-    const uint32_t bar_sched_full = bar_o_full + 16;              // [2] work-index slots, producer -> everyone
+    const uint32_t bar_o_staged = bar_o_full + 16;                // [tile] softmax warps -> store warp
+    const uint32_t bar_sched_full = bar_o_staged + 16;            // [2] work-index slots, producer -> everyone
     const uint32_t bar_sched_empty = bar_sched_full + 16;         // [2]
     const uint32_t tmem_slot = bar_sched_empty + 16;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -319,8 +334,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #endif
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_q_full, 1);
-        mbar_init(bar_q_empty, 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(bar_q_full + 8 * i, 1);
+            mbar_init(bar_q_empty + 8 * i, 2);        // last QK^T of the item retired + its O tiles stored
+        }
         for (int i = 0; i < C::kStages; i++) {
             mbar_init(bar_kv_full + 8 * i, 1);
             mbar_init(bar_kv_empty + 8 * i, 1);
@@ -330,10 +347,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             mbar_init(bar_p_full + 16 * t, 4);        // one arrival per softmax warp of the tile,
             mbar_init(bar_p_full + 16 * t + 8, 4);    // per half of P
             mbar_init(bar_o_full + 8 * t, 1);
+            mbar_init(bar_o_staged + 8 * t, 4);       // one arrival per softmax warp of the tile
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_sched_full + 8 * i, 1);
-            mbar_init(bar_sched_empty + 8 * i, 9);    // MMA warp + 8 softmax warps
+            mbar_init(bar_sched_empty + 8 * i, 10);   // MMA warp + 8 softmax warps + store warp
         }
         fence_mbar_init();
     }
@@ -345,6 +363,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
+        tma_prefetch_desc(&tmO);
     }
     tc_fence_before();
     __syncthreads();
@@ -398,13 +417,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const WorkItem wi = decode_work(w, p);
             const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
             const bool have_q1 = wi.q0 + kBlockM < p.Nq;
-            mbar_wait(bar_q_empty, (it & 1u) ^ 1u, 1);   // previous item's QK^T MMAs retired
+            // slot it&1 is free once the item two back has issued its last QK^T and stored its O tiles
+            mbar_wait(bar_q_empty + 8 * slot, ((it >> 1) & 1u) ^ 1u, 1);
             if (elect_one()) {
-                mbar_arrive_expect_tx(bar_q_full, (have_q1 ? 2 : 1) * C::kTileBytes);
+                mbar_arrive_expect_tx(bar_q_full + 8 * slot, (have_q1 ? 2 : 1) * C::kTileBytes);
                 for (int t = 0; t < (have_q1 ? 2 : 1); t++)
                     for (int pn = 0; pn < C::kPanels; pn++)
-                        tma_load_3d(sQ + t * C::kTileBytes + pn * C::kPanelBytes, &tmQ, bar_q_full, pn * 64,
-                                    wi.q0 + t * kBlockM, wi.bh);
+                        tma_load_3d(sQ + (slot * 2 + t) * C::kTileBytes + pn * C::kPanelBytes, &tmQ,
+                                    bar_q_full + 8 * slot, pn * 64, wi.q0 + t * kBlockM, wi.bh);
             }
             __syncwarp();
             for (int j = 0; j < nmax; j++) {
@@ -434,8 +454,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         uint32_t p_phase0 = 0u, p_phase1 = 0u;
         const uint32_t tS0 = tmem_base + C::kTmemS0, tS1 = tmem_base + C::kTmemS1;
         const uint32_t tO0 = tmem_base + C::kTmemO0, tO1 = tmem_base + C::kTmemO1;
-        const uint64_t qdesc0 = umma_smem_desc(sQ, 16, 1024);
-        const uint64_t qdesc1 = umma_smem_desc(sQ + C::kTileBytes, 16, 1024);
 
         // S_t = Q_t K_j^T : D/16 k-steps; k-step ks lives in panel ks/4 at byte offset (ks%4)*32
         auto issue_qk = [&](uint32_t tS, uint64_t qdesc, uint32_t k_smem, uint32_t bar) {
@@ -474,25 +492,38 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             __syncwarp();
         };
 
-        for (;; ++it) {
-            const int w = next_work(it);
-            if (w < 0) break;
-            const WorkItem wi = decode_work(w, p);
-            const int n0 = wi.n0, n1 = wi.n1;
-            const int nmax = n0 > n1 ? n0 : n1;
-            mbar_wait(bar_q_full, it & 1u, 10);
+        // First QK^T of an item (both tiles).  Issued one item ahead: right behind the previous item's
+        // last PV, while the softmax warps are still in that item's epilogue.
+        auto prologue = [&](uint32_t itn, const WorkItem& wn) {
+            const uint32_t slot = itn & 1u;
+            const int nm = wn.n0 > wn.n1 ? wn.n0 : wn.n1;
+            mbar_wait(bar_q_full + 8 * slot, (itn >> 1) & 1u, 10);
             tc_fence_after();
-            if (nmax > 0) {
+            if (nm > 0) {
                 mbar_wait(bar_kv_full + 8 * rk.idx, rk.phase, 11);
                 tc_fence_after();
                 const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
-                if (n0 > 0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
-                if (n1 > 0) issue_qk(tS1, qdesc1, k_smem, bar_s_full + 8);
+                if (wn.n0 > 0) issue_qk(tS0, umma_smem_desc(sQ + (slot * 2 + 0) * C::kTileBytes, 16, 1024), k_smem, bar_s_full);
+                if (wn.n1 > 0) issue_qk(tS1, umma_smem_desc(sQ + (slot * 2 + 1) * C::kTileBytes, 16, 1024), k_smem, bar_s_full + 8);
                 commit(bar_kv_empty + 8 * rk.idx);
                 rk.advance<C::kStages>(); rk.advance<C::kStages>();
             }
-            // Q is free for the next item as soon as the last QK^T of this one has retired
-            if (nmax <= 1) commit(bar_q_empty);
+            // the Q slot is released when the last QK^T of the item has retired (and its O tiles are stored)
+            if (nm <= 1) commit(bar_q_empty + 8 * slot);
+        };
+
+        int w = next_work(0);
+        WorkItem wi;
+        if (w >= 0) {
+            wi = decode_work(w, p);
+            prologue(0u, wi);
+        }
+        for (; w >= 0; ++it) {
+            const uint32_t slot = it & 1u;
+            const int n0 = wi.n0, n1 = wi.n1;
+            const int nmax = n0 > n1 ? n0 : n1;
+            const uint64_t qdesc0 = umma_smem_desc(sQ + (slot * 2 + 0) * C::kTileBytes, 16, 1024);
+            const uint64_t qdesc1 = umma_smem_desc(sQ + (slot * 2 + 1) * C::kTileBytes, 16, 1024);
             for (int j = 0; j < nmax; j++) {
                 const bool has_next = j + 1 < nmax;
                 mbar_wait(bar_kv_full + 8 * rv.idx, rv.phase, 12);
@@ -519,10 +550,44 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 if (has_next) {
                     commit(bar_kv_empty + 8 * rk.idx);
                     rk.advance<C::kStages>(); rk.advance<C::kStages>();
-                    if (j + 2 == nmax) commit(bar_q_empty);   // QK^T(nmax-1) was the last reader of Q
+                    if (j + 2 == nmax) commit(bar_q_empty + 8 * slot);   // QK^T(nmax-1) was the last reader of Q
                 }
             }
+            // next item: its Q pair is already resident in the other slot
+            w = next_work(it + 1u);
+            if (w >= 0) {
+                wi = decode_work(w, p);
+                prologue(it + 1u, wi);
+            }
         }
+    } else if (warp == kStoreWarp) {
+        // =============================== O tile store ===============================
+        // The softmax warps stage O_t / l as fp16 in the item's (now idle) Q tile buffers, 128B-swizzled;
+        // this warp hands them to TMA, which clips rows past Nq, and then returns the Q slot.
+        for (uint32_t it = 0;; ++it) {
+            const int w = next_work(it);
+            if (w < 0) break;
+            const WorkItem wi = decode_work(w, p);
+            const uint32_t slot = it & 1u;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                mbar_wait(bar_o_staged + 8 * t, it & 1u, 60 + t);
+                const int q_start = wi.q0 + t * kBlockM;
+                if (lane == 0 && !p.partial_mode && q_start < p.Nq) {   // one fixed lane: bulk-group state is per thread
+#pragma unroll
+                    for (int pn = 0; pn < C::kPanels; pn++)
+                        tma_store_3d(&tmO, sQ + (slot * 2 + t) * C::kTileBytes + pn * C::kPanelBytes, pn * 64, q_start, wi.bh);
+                    tma_store_commit();
+                }
+            }
+            if (lane == 0) {
+                tma_store_wait_read<0>();
+                mbar_arrive(bar_q_empty + 8 * slot);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+        __syncwarp();
     }
     } else {
         setmaxnreg_inc<kRegsSoftmax>();
@@ -543,7 +608,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
             const int q_start = wi.q0 + t * kBlockM;
-            if (q_start >= p.Nq) continue;                     // this Q tile does not exist
+            if (q_start >= p.Nq) {                             // this Q tile does not exist
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_o_staged + 8 * t);   // keep the store warp's phases in step
+                continue;
+            }
             const int n_t = t ? wi.n1 : wi.n0;
             const int row = q_start + row_in_tile;             // local query row
             // keys [0, lim) are visible to this row
@@ -589,7 +658,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const size_t grow = (size_t)wi.bh * p.Nq + row;
             if (!p.partial_mode) {
                 const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;   // FA.cu:502-503
-                __half* orow = p.o + grow * D;
+                // fp16 row -> staging tile = this item's Q tile buffer (every QK^T of the item has retired:
+                // o_full covers them), 16-byte chunks XOR-swizzled by row & 7 as TMA expects for SWIZZLE_128B
+                const uint32_t stage = sQ + ((it & 1u) * 2 + t) * C::kTileBytes + row_in_tile * 128;
 #pragma unroll
                 for (int c = 0; c < D; c += 32) {
                     uint32_t o[32];
@@ -600,23 +671,24 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
                         for (int i = 0; i < 32; i++) o[i] = 0u;
                     }
-                    if (row_ok) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            uint4 v;
-                            __half2 h;
-                            h = __floats2half2_rn(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
-                            v.x = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2half2_rn(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-                            v.y = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2half2_rn(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-                            v.z = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2half2_rn(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-                            v.w = *reinterpret_cast<uint32_t*>(&h);
-                            *reinterpret_cast<uint4*>(orow + c + i) = v;
-                        }
+                    for (int i = 0; i < 32; i += 8) {
+                        const int col = c + i;
+                        const uint32_t addr = stage + (col >> 6) * C::kPanelBytes + ((((col & 63) >> 3) ^ (row_in_tile & 7)) << 4);
+                        __half2 h;
+                        uint32_t v0, v1, v2, v3;
+                        h = __floats2half2_rn(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
+                        v0 = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2half2_rn(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                        v1 = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2half2_rn(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                        v2 = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2half2_rn(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+                        v3 = *reinterpret_cast<uint32_t*>(&h);
+                        st_shared_v4(addr, v0, v1, v2, v3);
                     }
                 }
+                fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
             } else {
                 // partial state (FA.cu:460-496): un-normalised fp32 O, (m, l) with m in the
                 // scaled-score (natural-log) domain; merge algebra of FA.cu:575-597 when accumulating
@@ -665,6 +737,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
             // O_t / S_t are free again: the next item's first P arrival orders after these reads
             tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_o_staged + 8 * t);   // store warp: tile staged (or written, in partial mode)
         }
     }
 
