@@ -106,8 +106,8 @@ struct Cfg {
     static constexpr int kBarPFull = kBarSFree + 2;              // [2][2] leader, index 2*b + half
     static constexpr int kBarPvDone = kBarPFull + 4;             // [2]   per CTA (multicast commit)
     static constexpr int kBarOFree = kBarPvDone + 2;             // [1]   leader
-    static constexpr int kBarOStaged = kBarOFree + 1;            // [1]   per CTA
-    static constexpr int kBarMReady = kBarOStaged + 1;           // [2][4] per CTA, index 4*set + quadrant
+    static constexpr int kBarOStaged = kBarOFree + 1;            // [2]   per CTA, one per Q slot
+    static constexpr int kBarMReady = kBarOStaged + 2;           // [2][4] per CTA, index 4*set + quadrant
     static constexpr int kBarSchedFull = kBarMReady + 8;         // [2]   per CTA
     static constexpr int kBarSchedEmpty = kBarSchedFull + 2;     // [2]   leader
     static constexpr int kNumBars = kBarSchedEmpty + 2;
@@ -477,6 +477,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
         mbar_init(bar(C::kBarOFree), 8 * CG);
         mbar_init(bar(C::kBarOStaged), 8);
+        mbar_init(bar(C::kBarOStaged + 1), 8);
         for (int i = 0; i < 8; i++) mbar_init(bar(C::kBarMReady + i), 1);
         fence_mbar_init();
     }
@@ -706,13 +707,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         // =============================== O tile store ===============================
         // Softmax warps stage O_t / l as fp16 in the (now idle) Q buffer of the unit, 128B-swizzled;
         // this warp hands it to TMA, which clips rows past Nq, and then returns the buffer.
+        uint32_t staged_parity = 0u;
         for (uint32_t it = 0;; ++it) {
             const int w = next_work(it);
             if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
             const uint32_t qslot = it & 1u;
             const int q_start = wi.q0 + (int)rank * kBlockM;
-            mbar_wait(bar(C::kBarOStaged), it & 1u, 60);
+            // one barrier per Q slot, waited only for units with tiles: it cannot complete twice before this
+            // warp has seen the first completion (the slot's next use needs the Q load this warp releases)
+            if (wi.n > 0) {
+                mbar_wait(bar(C::kBarOStaged + qslot), (staged_parity >> qslot) & 1u, 60);
+                staged_parity ^= 1u << qslot;
+            }
             const bool do_store = !p.partial_mode && wi.n > 0 && q_start < p.Nq;
             if (lane == 0) {   // one fixed lane: bulk-group state is per thread
                 if (do_store) {
@@ -910,7 +917,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(C::kBarOStaged));
+            if (have && lane == 0) mbar_arrive(bar(C::kBarOStaged + (it & 1u)));
             if (have) ++nz_units;
             g0 += (uint32_t)wi.n;
         }

@@ -82,7 +82,7 @@ struct Cfg {
     static constexpr int kSmemQ = 4 * kTileBytes;
     static constexpr int kSmemKV = kStages * kTileBytes;
     static constexpr int kBarOffset = kSmemQ + kSmemKV;
-    static constexpr int kNumBars = 4 + 2 * kStages + 8 + 2 + 4;
+    static constexpr int kNumBars = 4 + 2 * kStages + 8 + 4 + 4;
     static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 32 + 1024;  // +32: tmem slot, scheduler slots; +1024: manual alignment slack
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
     static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
@@ -315,8 +315,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t bar_s_full = bar_kv_empty + 8 * C::kStages;    // [tile]
     const uint32_t bar_p_full = bar_s_full + 16;                  // [tile][half]  index 2*t + h
     const uint32_t bar_o_full = bar_p_full + 32;                  // [tile]
-    const uint32_t bar_o_staged = bar_o_full + 16;                // [tile] softmax warps -> store warp
-    const uint32_t bar_sched_full = bar_o_staged + 16;            // [2] work-index slots, producer -> everyone
+    const uint32_t bar_o_staged = bar_o_full + 16;                // [Q slot][tile] softmax warps -> store warp
+    const uint32_t bar_sched_full = bar_o_staged + 32;            // [2] work-index slots, producer -> everyone
     const uint32_t bar_sched_empty = bar_sched_full + 16;         // [2]
     const uint32_t tmem_slot = bar_sched_empty + 16;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -347,7 +347,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             mbar_init(bar_p_full + 16 * t, 4);        // one arrival per softmax warp of the tile,
             mbar_init(bar_p_full + 16 * t + 8, 4);    // per half of P
             mbar_init(bar_o_full + 8 * t, 1);
-            mbar_init(bar_o_staged + 8 * t, 4);       // one arrival per softmax warp of the tile
+            mbar_init(bar_o_staged + 8 * t, 4);       // one arrival per softmax warp of the tile,
+            mbar_init(bar_o_staged + 8 * (2 + t), 4); // per Q slot
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_sched_full + 8 * i, 1);
@@ -564,6 +565,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         // =============================== O tile store ===============================
         // The softmax warps stage O_t / l as fp16 in the item's (now idle) Q tile buffers, 128B-swizzled;
         // this warp hands them to TMA, which clips rows past Nq, and then returns the Q slot.
+        uint32_t staged_parity = 0u;      // bit (slot*2 + tile): parity of that barrier's next completion
         for (uint32_t it = 0;; ++it) {
             const int w = next_work(it);
             if (w < 0) break;
@@ -571,9 +573,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const uint32_t slot = it & 1u;
 #pragma unroll
             for (int t = 0; t < 2; t++) {
-                mbar_wait(bar_o_staged + 8 * t, it & 1u, 60 + t);
                 const int q_start = wi.q0 + t * kBlockM;
-                if (lane == 0 && !p.partial_mode && q_start < p.Nq) {   // one fixed lane: bulk-group state is per thread
+                if (q_start >= p.Nq) continue;                          // tile absent: nobody arrives, nothing to store
+                const uint32_t b = slot * 2 + t;
+                mbar_wait(bar_o_staged + 8 * b, (staged_parity >> b) & 1u, 60 + t);
+                staged_parity ^= 1u << b;
+                if (lane == 0 && !p.partial_mode) {                     // one fixed lane: bulk-group state is per thread
 #pragma unroll
                     for (int pn = 0; pn < C::kPanels; pn++)
                         tma_store_3d(&tmO, sQ + (slot * 2 + t) * C::kTileBytes + pn * C::kPanelBytes, pn * 64, q_start, wi.bh);
@@ -608,11 +613,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
             const int q_start = wi.q0 + t * kBlockM;
-            if (q_start >= p.Nq) {                             // this Q tile does not exist
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_o_staged + 8 * t);   // keep the store warp's phases in step
-                continue;
-            }
+            if (q_start >= p.Nq) continue;                     // this Q tile does not exist (the store warp knows)
             const int n_t = t ? wi.n1 : wi.n0;
             const int row = q_start + row_in_tile;             // local query row
             // keys [0, lim) are visible to this row
@@ -738,7 +739,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             // O_t / S_t are free again: the next item's first P arrival orders after these reads
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_o_staged + 8 * t);   // store warp: tile staged (or written, in partial mode)
+            // store warp: tile staged (or written out, in partial mode).  One barrier per (Q slot, tile):
+            // it cannot complete twice before the store warp has seen the first completion, because the
+            // slot's next use needs the Q load that the store warp itself releases.
+            if (lane == 0) mbar_arrive(bar_o_staged + 8 * ((it & 1u) * 2 + t));
         }
     }
 
