@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "flash_attn_fwd",
     "flash_attn_fwd_ex",
     "flash_attn_finalize",
+    "flash_attn_merge",
     "flash_attn_fwd_host",
     "flash_attn_get_kernel_info",
     "flash_attn_set_sm_margin",
@@ -92,6 +93,9 @@ def lib() -> ctypes.CDLL:
     L.flash_attn_fwd_ex.restype = ci
     L.flash_attn_finalize.argtypes = [vp, vp, vp, ll, ci, vp]
     L.flash_attn_finalize.restype = ci
+    if hasattr(L, "flash_attn_merge"):   # absent from archived A/B builds of older kernels
+        L.flash_attn_merge.argtypes = [vp, vp, vp, ci, ll, ci, vp]
+        L.flash_attn_merge.restype = ci
     L.flash_attn_fwd_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci]
     L.flash_attn_fwd_host.restype = ci
     L.flash_attn_get_kernel_info.argtypes = [ci, ci, ci, ci, ci, ctypes.POINTER(KernelInfo)]
@@ -172,6 +176,18 @@ def flash_attn_finalize(o_partial, ml, out, stream=None):
     with torch.cuda.device(out.device):
         rc = lib().flash_attn_finalize(o_partial.data_ptr(), ml.data_ptr(), out.data_ptr(), rows,
                                        o_partial.shape[-1], _stream_ptr(stream))
+    check(rc)
+    return out
+
+
+def flash_attn_merge(o_partials, mls, out, stream=None):
+    """Merge `splits` partial states (o_partials [S, rows, D] fp32, mls [S, rows, 2]) into the FP16 tensor `out`."""
+    import torch
+    S, rows, D = o_partials.shape
+    assert mls.shape == (S, rows, 2) and o_partials.is_contiguous() and mls.is_contiguous()
+    with torch.cuda.device(out.device):
+        rc = lib().flash_attn_merge(o_partials.data_ptr(), mls.data_ptr(), out.data_ptr(), S, rows, D,
+                                    _stream_ptr(stream))
     check(rc)
     return out
 

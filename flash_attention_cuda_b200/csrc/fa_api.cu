@@ -311,6 +311,21 @@ int flash_attn_finalize(const float* o_partial, const float* ml, void* o, long l
     return (int)cudaGetLastError();
 }
 
+int flash_attn_merge(const float* o_partial, const float* ml, void* o, int splits, long long rows, int D,
+                     void* stream) {
+    if (!o_partial || !ml || !o) return FA_ERR_NULL_PTR;
+    if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+    if (rows < 1 || splits < 1) return FA_ERR_BAD_SHAPE;
+    const long long threads = rows * (D / 4);
+    const int block = 256;
+    const long long grid = (threads + block - 1) / block;
+    if (grid > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
+    fa::fa_merge_kernel<<<(unsigned)grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        o_partial, ml, static_cast<__half*>(o), rows, D, splits);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho, int B, int H, int N, int D,
                         int causal) {
     if (!hq || !hk || !hv || !ho) return FA_ERR_NULL_PTR;

@@ -696,7 +696,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 float m_out = (m_ref == -INFINITY) ? -FLT_MAX : m_ref * p.scale;
                 float l_out = l_run;
                 float w_new = 1.f, w_old = 0.f;
-                float* prow = p.o_partial + grow * D;
                 if (p.accumulate && row_ok) {
                     const float m_old = p.ml[grow * 2 + 0];
                     const float l_old = p.ml[grow * 2 + 1];
@@ -707,29 +706,59 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     l_out = l_old * w_old + l_run * w_new;
                     m_out = m_max;
                 }
+                // The fp32 rows go through this warp's slice of the item's idle Q tile buffer and leave it
+                // transposed: one thread per row would touch 16 bytes every 4*D bytes of global memory (the
+                // accumulate form cost +25 % per ring hop kernel that way), whereas 4*D/2-byte row segments
+                // per group of lanes are whole sectors.  D/2 columns per pass; 16-byte chunks XOR-swizzled by
+                // row so that both the row-wise writes and the transposed reads are bank-conflict free.
+                constexpr int kW = D / 2;                  // fp32 columns per pass
+                constexpr int kCPR = kW / 4;               // 16-byte chunks per staged row = lanes per row on the way out
+                constexpr int kRPI = 32 / kCPR;            // rows one warp instruction covers on the way out
+                const uint32_t wstage = sQ + ((it & 1u) * 2 + t) * C::kTileBytes + (uint32_t)(warp & 3) * (32 * kW * 4);
+                const int warp_row0 = q_start + (warp & 3) * 32;
+                float* const gbase = p.o_partial + ((size_t)wi.bh * p.Nq + warp_row0) * D;
 #pragma unroll
-                for (int c = 0; c < D; c += 32) {
-                    uint32_t o[32];
-                    if (n_t > 0) {
-                        tmem_ld_x32(tO + c, o);
-                        tmem_wait_ld();
-                    } else {
+                for (int ps = 0; ps < 2; ps++) {
 #pragma unroll
-                        for (int i = 0; i < 32; i++) o[i] = 0u;
-                    }
-                    if (row_ok) {
+                    for (int c = 0; c < kW; c += 32) {
+                        uint32_t o[32];
+                        if (n_t > 0) {
+                            tmem_ld_x32(tO + ps * kW + c, o);
+                            tmem_wait_ld();
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; i++) o[i] = 0u;
+                        }
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            float4 v = make_float4(__uint_as_float(o[i]) * w_new, __uint_as_float(o[i + 1]) * w_new,
-                                                   __uint_as_float(o[i + 2]) * w_new, __uint_as_float(o[i + 3]) * w_new);
-                            if (p.accumulate) {
-                                const float4 old = *reinterpret_cast<const float4*>(prow + c + i);
-                                v.x += old.x * w_old; v.y += old.y * w_old;
-                                v.z += old.z * w_old; v.w += old.w * w_old;
-                            }
-                            *reinterpret_cast<float4*>(prow + c + i) = v;
+                            const int ch = (c + i) >> 2;
+                            st_shared_v4(wstage + lane * (kW * 4) + ((ch ^ (lane & (kCPR - 1))) << 4),
+                                         __float_as_uint(__uint_as_float(o[i]) * w_new), __float_as_uint(__uint_as_float(o[i + 1]) * w_new),
+                                         __float_as_uint(__uint_as_float(o[i + 2]) * w_new), __float_as_uint(__uint_as_float(o[i + 3]) * w_new));
                         }
                     }
+                    __syncwarp();
+                    const int ch = lane & (kCPR - 1);
+                    // all loads of the old partial first (they are independent: one round trip, not kCPR)
+                    float4 old[kCPR];
+#pragma unroll
+                    for (int i = 0; i < kCPR; i++) {
+                        const int rr = i * kRPI + lane / kCPR;          // row within this warp's 32
+                        old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.accumulate && warp_row0 + rr < p.Nq)
+                            old[i] = __ldcg(reinterpret_cast<const float4*>(gbase + (size_t)rr * D + ps * kW + ch * 4));
+                    }
+#pragma unroll
+                    for (int i = 0; i < kCPR; i++) {
+                        const int rr = i * kRPI + lane / kCPR;
+                        float4 v = ld_shared_v4f(wstage + rr * (kW * 4) + ((ch ^ (rr & (kCPR - 1))) << 4));
+                        const float wo = __shfl_sync(0xffffffffu, w_old, rr);
+                        v.x += old[i].x * wo; v.y += old[i].y * wo;
+                        v.z += old[i].z * wo; v.w += old[i].w * wo;
+                        if (warp_row0 + rr < p.Nq)
+                            *reinterpret_cast<float4*>(gbase + (size_t)rr * D + ps * kW + ch * 4) = v;
+                    }
+                    __syncwarp();   // the slice is rewritten by the next pass
                 }
                 if (row_ok) {
                     p.ml[grow * 2 + 0] = m_out;
@@ -787,6 +816,38 @@ __global__ void fa_finalize_kernel(const float* __restrict__ o_partial, const fl
     const float4 v = *reinterpret_cast<const float4*>(o_partial + r * D + c);
     __half2 a = __floats2half2_rn(v.x * inv, v.y * inv);
     __half2 b = __floats2half2_rn(v.z * inv, v.w * inv);
+    uint2 out;
+    out.x = *reinterpret_cast<uint32_t*>(&a);
+    out.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(o + r * D + c) = out;
+}
+
+// fp16 O = sum_s w_s O_s / sum_s w_s l_s with w_s = exp(m_s - max_s m_s): the reference's
+// flash_attention_splitk_merge (FA.cu:559-598, never launched there) over `splits` partial states laid
+// out [split][row][D] / [split][row][2].  Used by ring context parallelism: every chunk pair writes its
+// own partial (write-only) and one pass merges them, instead of a read-modify-write per hop.
+__global__ void fa_merge_kernel(const float* __restrict__ o_partial, const float* __restrict__ ml,
+                                __half* __restrict__ o, long long rows, int D, int splits) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
+    const int per_row = D / 4;
+    const long long r = idx / per_row;
+    if (r >= rows) return;
+    const int c = (int)(idx % per_row) * 4;
+    float m_max = -FLT_MAX;
+    for (int s = 0; s < splits; s++) m_max = fmaxf(m_max, ml[((long long)s * rows + r) * 2]);
+    float l = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; s++) {
+        const float m_s = ml[((long long)s * rows + r) * 2];
+        const float l_s = ml[((long long)s * rows + r) * 2 + 1];
+        const float w = (m_s <= -FLT_MAX) ? 0.f : exp2f((m_s - m_max) * 1.4426950408889634f);   // FA.cu:583-586
+        const float4 v = *reinterpret_cast<const float4*>(o_partial + ((long long)s * rows + r) * D + c);
+        l += w * l_s;
+        acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    }
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    __half2 a = __floats2half2_rn(acc.x * inv, acc.y * inv);
+    __half2 b = __floats2half2_rn(acc.z * inv, acc.w * inv);
     uint2 out;
     out.x = *reinterpret_cast<uint32_t*>(&a);
     out.y = *reinterpret_cast<uint32_t*>(&b);

@@ -5,9 +5,11 @@
 * ring context parallelism (config 5): the sequence is cut into 2P chunks, rank r owns chunks r and
   2P-1-r (zig-zag: every hop costs every rank exactly two unmasked chunk pairs under a causal mask);
   Q and the partial state stay, K/V chunk pairs travel around the ring with send/recv on a side
-  stream while the current pair is being consumed.  Per-hop math is `flash_attn_fwd_ex`, which
-  accumulates (O un-normalised fp32, m, l) in place with the merge algebra of the reference's split-K
-  code (flash_attention.cu:460-496, 575-597); `flash_attn_finalize` writes O = o_partial / l.
+  stream while the current pair is being consumed.  Per-hop math is `flash_attn_fwd_ex`: every chunk
+  pair writes its own partial state (O un-normalised fp32, m, l) in the format of the reference's
+  split-K code (flash_attention.cu:460-496), and `flash_attn_merge` -- the reference's
+  flash_attention_splitk_merge, flash_attention.cu:559-598 -- combines them into O at the end.  (A
+  read-modify-write of one running state per pair costs +25 % per kernel; write-only costs +5 %.)
 
 The compute callables are injectable so the schedule and the send/recv plumbing can be exercised on CPU
 with gloo (tests/test_ring_cpu.py); the defaults are the CUDA library and nothing else.
@@ -59,9 +61,9 @@ def _cuda_partial(q, k, v, o_partial, ml, causal, q_offset, kv_offset, accumulat
     flash_attn_fwd_partial(q, k, v, o_partial, ml, causal, q_offset, kv_offset, accumulate)
 
 
-def _cuda_finalize(o_partial, ml, out):
-    from . import flash_attn_finalize
-    flash_attn_finalize(o_partial, ml, out)
+def _cuda_finalize(o_partials, mls, out):
+    from . import flash_attn_merge
+    flash_attn_merge(o_partials, mls, out)
 
 
 def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, group=None, *,
@@ -83,20 +85,23 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
     dev = q[0].device
     on_cuda = dev.type == "cuda"
 
-    # partial state and receive buffers are cached per (device, shape): a ring step allocates nothing.
-    # No zero-fill either: the first chunk pair of a Q chunk runs with accumulate = False and overwrites.
-    key = (str(dev), B, H, C, D, q[0].dtype, world > 1)
+    # Which chunk pairs does this rank compute, hop by hop?  (deterministic: every rank can enumerate it)
+    schedule = [hop_pairs(rank, (rank - hop) % world, world, causal) for hop in range(world)]
+    n_split = [max(1, sum(1 for hp in schedule for (qi, _, _) in hp if qi == i)) for i in range(2)]
+    # partial states (one per chunk pair, write-only) and receive buffers are cached per (device, shape):
+    # a ring step allocates nothing and zero-fills nothing
+    key = (str(dev), B, H, C, D, q[0].dtype, world, bool(causal))
     ws = _workspace.get(key)
     if ws is None:
         ws = {
-            "o_part": [torch.empty((B * H * C, D), dtype=torch.float32, device=dev) for _ in range(2)],
-            "ml": [torch.empty((B * H * C, 2), dtype=torch.float32, device=dev) for _ in range(2)],
+            "o_part": [torch.empty((n_split[i], B * H * C, D), dtype=torch.float32, device=dev) for i in range(2)],
+            "ml": [torch.empty((n_split[i], B * H * C, 2), dtype=torch.float32, device=dev) for i in range(2)],
             "recv": [[torch.empty_like(k[0]) for _ in range(4)] for _ in range(2)] if world > 1 else None,
         }
         _workspace.clear()          # one shape at a time: the buffers are large
         _workspace[key] = ws
     o_part, ml = ws["o_part"], ws["ml"]
-    started = [False, False]
+    used = [0, 0]          # partial states written so far, per Q chunk
 
     cur = [k[0], k[1], v[0], v[1]]
     # two receive sets: hop h receives into set h & 1 while set (h - 1) & 1 (or the caller's k, v) is read
@@ -127,10 +132,10 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
             else:
                 reqs = dist.batch_isend_irecv(ops)
         kb = zigzag_chunks(src, world)
-        for qi, ki, diag in hop_pairs(rank, src, world, causal):
-            partial(q[qi], cur[ki], cur[2 + ki], o_part[qi], ml[qi], bool(diag),
-                    qa[qi] * C, kb[ki] * C, started[qi])
-            started[qi] = True
+        for qi, ki, diag in schedule[hop]:
+            partial(q[qi], cur[ki], cur[2 + ki], o_part[qi][used[qi]], ml[qi][used[qi]], bool(diag),
+                    qa[qi] * C, kb[ki] * C, False)
+            used[qi] += 1
         if hop + 1 < world:
             for r in reqs:
                 r.wait()
@@ -143,5 +148,8 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
         set_sm_margin(old_margin)
     out = [torch.empty_like(q[0]), torch.empty_like(q[1])]
     for i in range(2):
-        finalize(o_part[i], ml[i], out[i])
+        if used[i] == 0:           # a Q chunk that saw no key at all (cannot happen with the zig-zag layout)
+            out[i].zero_()
+        else:
+            finalize(o_part[i][:used[i]], ml[i][:used[i]], out[i])
     return out

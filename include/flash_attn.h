@@ -55,6 +55,13 @@ int flash_attn_fwd_ex(const void* q, const void* k, const void* v, float* o_part
                       long long kv_offset, int accumulate, void* stream);
 int flash_attn_finalize(const float* o_partial, const float* ml, void* o, long long rows, int D,
                         void* stream);
+/* The reference's flash_attention_splitk_merge (FA.cu:559-598; defined there, never launched): merges
+ * `splits` independent partial states, o_partial [splits][rows][D] and ml [splits][rows][2] (each written
+ * by a flash_attn_fwd_ex call with accumulate = 0), into FP16 O = sum_s w_s O_s / sum_s w_s l_s,
+ * w_s = exp(m_s - max m).  One write-only partial per K/V block plus one merge is cheaper than a
+ * read-modify-write of the running state per block. */
+int flash_attn_merge(const float* o_partial, const float* ml, void* o, int splits, long long rows, int D,
+                     void* stream);
 
 /* The reference harness's call pattern with HOST buffers (FA.cu:771-780): H2D of Q,K,V,
  * dispatch, D2H of O, on a per-device cached staging workspace.  Blocks until O is on the host. */

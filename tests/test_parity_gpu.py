@@ -202,6 +202,28 @@ def test_partial_state_and_merge_equals_monolithic(fa):
     gate(out.cpu().numpy(), ref, "4-block KV merge")
 
 
+@pytest.mark.parametrize("D,causal", [(128, 1), (64, 0)])
+def test_write_only_partials_and_splitk_merge(fa, D, causal):
+    # the reference's split-K design (FA.cu:460-496 partials, 559-598 merge), live: every KV block writes its
+    # own partial state, flash_attn_merge combines them; includes a block the causal mask hides completely
+    B, H, N, P = 2, 3, 640, 5
+    q, k, v = normal((B, H, N, D), seed=33 + D)
+    ref = _oracle.attention(q, k, v, causal)
+    tq, tk, tv = (torch.from_numpy(x).cuda() for x in (q, k, v))
+    o_parts = torch.full((P, B * H * N, D), float("nan"), dtype=torch.float32, device="cuda")
+    mls = torch.full((P, B * H * N, 2), float("nan"), dtype=torch.float32, device="cuda")
+    blk = N // P
+    for s in range(P):
+        ks = tk[:, :, s * blk:(s + 1) * blk].contiguous()
+        vs = tv[:, :, s * blk:(s + 1) * blk].contiguous()
+        fa.flash_attn_fwd_partial(tq, ks, vs, o_parts[s], mls[s], bool(causal), 0, s * blk, accumulate=False)
+    out = torch.empty_like(tq)
+    fa.flash_attn_merge(o_parts, mls, out)
+    torch.cuda.synchronize()
+    assert not fa.watchdog_status()["aborted"]
+    gate(out.cpu().numpy(), ref, f"{P}-block write-only partials + merge, D={D}")
+
+
 def test_host_buffer_entry_point(fa):
     q, k, v = normal((1, 2, 384, 128), seed=41)
     out = np.empty_like(q)
@@ -297,7 +319,7 @@ def test_experimental_pair_kernel_passes_the_same_parity_tests(fa):
     import sys
     env = dict(os.environ, FLASH_ATTN_B200_KERNEL="pair")
     keep = ("reference_harness or causal_long or ragged or head_dim_64 or batch_greater or rescale or row0 or v_ones "
-            "or linearity or golden or partial_state or canaries or many_heads or full_size_row_sampled")
+            "or linearity or golden or partial_state or splitk_merge or canaries or many_heads or full_size_row_sampled")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k", keep],
                        env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]

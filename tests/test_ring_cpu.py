@@ -1,7 +1,7 @@
 """CPU-only, world_size 2 over gloo: the multi-GPU host logic of flash_attention_cuda_b200/ring.py.
 
 The ring driver is run for real (zig-zag ownership, hop schedule, double-buffered send/recv of K/V
-chunk pairs, in-place accumulation of partial states, finalize); only the per-hop math is injected as a
+chunk pairs, one partial state per chunk pair, final merge); only the per-hop math is injected as a
 numpy stand-in with the semantics of flash_attn_fwd_ex, so this needs no GPU.  The result is gated
 against the monolithic CPU oracle."""
 import os
@@ -58,10 +58,15 @@ def np_partial(q, k, v, o_part, ml, causal, q_off, kv_off, accumulate):
             mlv[:, 1] = l_new
 
 
-def np_finalize(o_part, ml, out):
-    l = ml[:, 1:2]
-    res = torch.where(l > 0, o_part / l, torch.zeros_like(o_part))
-    out.copy_(res.reshape(out.shape).half())
+def np_finalize(o_parts, mls, out):
+    """numpy stand-in for flash_attn_merge (FA.cu:559-598): o_parts [S, rows, D], mls [S, rows, 2]."""
+    op, m, l = o_parts.numpy(), mls[:, :, 0].numpy(), mls[:, :, 1].numpy()
+    m_max = m.max(axis=0)
+    w = np.where(m <= -FLT_MAX, 0.0, np.exp(m - m_max[None, :])).astype(np.float32)
+    lsum = (w * l).sum(axis=0)
+    acc = (w[:, :, None] * op).sum(axis=0)
+    res = np.where(lsum[:, None] > 0, acc / np.maximum(lsum[:, None], 1e-30), 0.0).astype(np.float32)
+    out.copy_(torch.from_numpy(res).reshape(out.shape).half())
 
 
 def _worker(rank, world, port, causal, N, D, H, ret):
