@@ -59,11 +59,13 @@ void load_encode_fn() {
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
 }
 
-template <int D>
+template <int D, int kPoly>
 int set_kernel_attrs() {
-    return (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D, kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      fa::Cfg<D>::kSmemBytes);
 }
+// exp2 on the FMA pipe for 1 pair in 4 only where it pays: D = 128 and at least 32 KV tiles (fa_fwd_sm100.cuh)
+bool use_poly(int D, int Nkv) { return D == 128 && Nkv >= 4096; }
 template <int D, int CG>
 int set_pair_kernel_attrs() {
     return (int)cudaFuncSetAttribute(fa_pair::fa_fwd_kernel<D, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -105,8 +107,9 @@ DeviceState* device_state(int* err) {
         st->num_sms = prop.multiProcessorCount;
         st->cc_major = prop.major;
         if (prop.major != 10) { st->ok = FA_ERR_UNSUPPORTED_ARCH; return; }
-        int r = set_kernel_attrs<128>();
-        if (r == 0) r = set_kernel_attrs<64>();
+        int r = set_kernel_attrs<128, 1>();
+        if (r == 0) r = set_kernel_attrs<128, 0>();
+        if (r == 0) r = set_kernel_attrs<64, 0>();
         if (r == 0 && use_pair_kernel()) {
             r = set_pair_kernel_attrs<128, 1>();
             if (r == 0) r = set_pair_kernel_attrs<128, 2>();
@@ -166,7 +169,7 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     return p;
 }
 
-template <int D>
+template <int D, int kPoly>
 int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
            const CUtensorMap& to, fa::Params p, cudaStream_t stream) {
     int avail = st->num_sms - g_sm_margin.load(std::memory_order_relaxed);
@@ -187,7 +190,7 @@ int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D>, tq, tk, tv, to, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D, kPoly>, tq, tk, tv, to, p);
     if (le != cudaSuccess) return (int)le;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();   // FA.cu:662
@@ -267,7 +270,8 @@ int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaS
     if ((rc = make_tmap(&tv, v, p.BH, p.Nkv, D)) != FA_OK) return rc;
     // O store map (unused in partial mode: describe Q's extent on a valid pointer)
     if ((rc = make_tmap(&to, p.o ? (const void*)p.o : q, p.BH, p.Nq, D)) != FA_OK) return rc;
-    return D == 128 ? launch<128>(st, tq, tk, tv, to, p, stream) : launch<64>(st, tq, tk, tv, to, p, stream);
+    if (D == 64) return launch<64, 0>(st, tq, tk, tv, to, p, stream);
+    return use_poly(D, p.Nkv) ? launch<128, 1>(st, tq, tk, tv, to, p, stream) : launch<128, 0>(st, tq, tk, tv, to, p, stream);
 }
 
 }  // namespace
@@ -394,8 +398,9 @@ int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_att
     if (B < 1 || H < 1 || N < 1) return FA_ERR_BAD_SHAPE;
     memset(info, 0, sizeof *info);
     cudaFuncAttributes attr;
-    cudaError_t e = D == 128 ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128>)
-                             : cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<64>);
+    cudaError_t e = D == 64            ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<64, 0>)
+                    : use_poly(D, N) ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, 1>)
+                                     : cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, 0>);
     if (e != cudaSuccess) return (int)e;
     int err = 0;
     DeviceState* st = device_state(&err);

@@ -58,14 +58,14 @@ constexpr int kStoreWarp = 10;
 constexpr int kTmemCols = 512;
 constexpr int kRegsSoftmax = 208;   // setmaxnreg: softmax warpgroups grow, the producer/MMA warpgroup shrinks
 constexpr int kRegsOther = 80;      // 2*128*208 + 128*80 = 63488 <= 168 (launch) * 384
-constexpr float kRescaleThreshold = 8.0f;
+constexpr float kRescaleThreshold = 8.0f;   // lazy rescale: tolerate P up to 2^8 before moving the reference max
 // Of every 4 element pairs, this many take exp2 on the FMA pipe (Cody-Waite + degree-3 minimax)
 // instead of MUFU.EX2: at 16 MUFU/clk/SM the 16384 exponentials of a 128x128 tile cost as many
 // cycles as its two MMAs, so the SFU -- not the tensor core -- would set the pace.
-#ifndef FA_POLY_PAIRS
-#define FA_POLY_PAIRS 1
-#endif
-constexpr int kPolyPairs = FA_POLY_PAIRS;  // lazy rescale: tolerate P up to 2^8 before moving the reference max
+// Template parameter kPoly of the kernel: of every 4 element pairs, this many take exp2 on the FMA pipe.
+// 1 pays off only when the loop runs long enough for MUFU throughput to matter (D=128, N >= 4096: +1.4 %);
+// for shorter sequences and D=64 the extra ~140 instructions per tile cost more than the 32 MUFU they
+// save (causal N=2048: 722 vs 664 TFLOPS, D=64: 689 vs 676 -- profiles/r01_v4b_poly_ab.log), and 2 loses everywhere.
 
 template <int D>
 struct Cfg {
@@ -189,6 +189,7 @@ __device__ __forceinline__ void exp2_pair(uint64_t x2, float& p0, float& p1) {
 }
 
 // exponentials + fp16 packing of 64 consecutive columns (one half of the tile)
+template <int kPoly>
 __device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64_t scale2, uint64_t neg2,
                                          uint64_t& sum_a, uint64_t& sum_b) {
 #pragma unroll
@@ -202,7 +203,7 @@ __device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64
 #ifdef FA_SKELETON
             unpack_f32x2(x2, p0, p1);
 #else
-            if (q < kPolyPairs) exp2_pair<true>(x2, p0, p1);
+            if (q < kPoly) exp2_pair<true>(x2, p0, p1);
             else exp2_pair<false>(x2, p0, p1);
 #endif
             if (q & 1) sum_b = add_f32x2(sum_b, pack_f32x2(p0, p1));   // row sum of the un-rounded p (FA.cu:273-279)
@@ -214,7 +215,7 @@ __device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64
 }
 
 // ---- softmax of one 128x128 S tile; one thread owns one row ----
-template <int D, bool kMask>
+template <int D, bool kMask, int kPoly>
 __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
                                              uint32_t bar_o_full, int lim_local, bool have_o,
                                              uint32_t pv_count, float& m_ref, float& l_run) {
@@ -285,7 +286,7 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     // keys 0-63 -> columns [0,32) -> barrier half 0, keys 64-127 -> columns [32,64) -> half 1
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        exp_half(s + 64 * h, pk, scale2, neg2, sum_a, sum_b);
+        exp_half<kPoly>(s + 64 * h, pk, scale2, neg2, sum_a, sum_b);
         tmem_st_x32(tS + 32 * h, pk);
         tmem_wait_st();
         tc_fence_before();
@@ -297,7 +298,7 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     l_run += a0 + a1;
 }
 
-template <int D>
+template <int D, int kPoly>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
@@ -636,9 +637,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 const int k0 = j * kBlockN;
                 const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
                 if (need_mask)
-                    softmax_tile<D, true>(p, tS, tO, my_p_full, my_o_full, lim - k0, j > 0, pv_count, m_ref, l_run);
+                    softmax_tile<D, true, kPoly>(p, tS, tO, my_p_full, my_o_full, lim - k0, j > 0, pv_count, m_ref, l_run);
                 else
-                    softmax_tile<D, false>(p, tS, tO, my_p_full, my_o_full, kBlockN, j > 0, pv_count, m_ref, l_run);
+                    softmax_tile<D, false, kPoly>(p, tS, tO, my_p_full, my_o_full, kBlockN, j > 0, pv_count, m_ref, l_run);
                 ++pv_count;
 #ifdef FA_TIMING
                 if (lane == 0 && (warp & 3) == 0 && j > 0 && (j & 7) == 0) {   // sampled: 1 tile in 8
