@@ -190,8 +190,17 @@ def bench_ring(args, workload, rank, world, local_rank, barrier):
         o = torch.empty_like(q)
         step = lambda: fa.flash_attn_fwd(q, k, v, causal=bool(causal), out=o)
     else:
-        q, k, v = ([mk(C), mk(C)] for _ in range(3))
-        step = lambda: ring.ring_attention_forward(q, k, v, bool(causal))
+        exchange = args.ring_exchange
+        q = [mk(C), mk(C)]
+        if exchange == "pull":
+            # K/V live in peer-readable memory from the start (no staging copy inside the step)
+            px = ring.peer_kv(B, H, C, D, torch.device("cuda", local_rank))
+            for t in px.k + px.v:
+                t.copy_(mk(C))
+            k, v = px.k, px.v
+        else:
+            k, v = [mk(C), mk(C)], [mk(C), mk(C)]
+        step = lambda: ring.ring_attention_forward(q, k, v, bool(causal), exchange=exchange)
     steps, warm = max(2, min(args.steps, 5)), 2
     for _ in range(warm):
         step()
@@ -215,8 +224,11 @@ def bench_ring(args, workload, rank, world, local_rank, barrier):
             "steps": steps, "warmup": warm, "ms_per_step": round(ms, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": args.workload, "B": B, "H": H, "N": N, "D": D, "causal": causal,
-                       "parallelism": f"ring-cp{world} zig-zag, NCCL send/recv of K/V chunk pairs "
-                                      f"({4 * B * H * C * D * 2 / 2**20:.0f} MiB per hop per rank)" if world > 1
+                       "parallelism": (f"cp{world} zig-zag, "
+                                       + ("copy-engine pulls of the unmasked K/V chunks from the owner's HBM "
+                                          "(flash_attn_peer_copy), no communication kernel"
+                                          if args.ring_exchange == "pull" else "NCCL send/recv of K/V chunk pairs")
+                                       + f" (<= {4 * B * H * C * D * 2 / 2**20:.0f} MiB per hop per rank)") if world > 1
                        else "single GPU, monolithic kernel"},
             "roofline": {"bound": "tensor", "achieved": round(fl / (ms * 1e-3) / 1e12 / world, 2),
                          "peak": pk["tflops_sustained"] or pk["tflops"], "unit": "TFLOP/s",
@@ -224,6 +236,7 @@ def bench_ring(args, workload, rank, world, local_rank, barrier):
                          "traffic": None, "peak_source": pk["source"] + ", cuBLAS bf16 sustained (long step)"},
             "gpu_launches": None}))
     if world > 1:
+        ring.release_peer_kv()
         dist.destroy_process_group()
 
 
@@ -233,6 +246,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
+    ap.add_argument("--ring-exchange", default="pull", choices=["pull", "sendrecv"],
+                    help="cfg5 only: how the ranks get at each other's K/V (flash_attention_cuda_b200/ring.py)")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--sweep", action="store_true", help="also print the README-style TFLOPS table to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")

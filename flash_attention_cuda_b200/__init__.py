@@ -40,6 +40,11 @@ EXPORTED_SYMBOLS = (
     "flash_attn_fwd_host",
     "flash_attn_get_kernel_info",
     "flash_attn_set_sm_margin",
+    "flash_attn_peer_alloc",
+    "flash_attn_peer_open",
+    "flash_attn_peer_close",
+    "flash_attn_peer_free",
+    "flash_attn_peer_copy",
     "flash_attn_launch_count",
     "flash_attn_destroy",
     "flash_attn_error_string",
@@ -103,6 +108,15 @@ def lib() -> ctypes.CDLL:
     if hasattr(L, "flash_attn_set_sm_margin"):   # absent from archived A/B builds of older kernels
         L.flash_attn_set_sm_margin.argtypes = [ci]
         L.flash_attn_set_sm_margin.restype = ci
+    if hasattr(L, "flash_attn_peer_alloc"):   # absent from archived A/B builds of older kernels
+        L.flash_attn_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
+        L.flash_attn_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.flash_attn_peer_close.argtypes = [vp]
+        L.flash_attn_peer_free.argtypes = [vp]
+        L.flash_attn_peer_copy.argtypes = [vp, vp, ctypes.c_size_t, vp]
+        for f in (L.flash_attn_peer_alloc, L.flash_attn_peer_open, L.flash_attn_peer_close,
+                  L.flash_attn_peer_free, L.flash_attn_peer_copy):
+            f.restype = ci
     L.flash_attn_launch_count.argtypes = []
     L.flash_attn_launch_count.restype = ctypes.c_ulonglong
     L.flash_attn_destroy.argtypes = []
@@ -208,6 +222,53 @@ def watchdog_status() -> dict:
 def set_sm_margin(sms: int) -> int:
     """Leave `sms` SMs free in every later launch (room for NCCL kernels); returns the previous value."""
     return int(lib().flash_attn_set_sm_margin(int(sms)))
+
+
+PEER_HANDLE_BYTES = 64
+
+
+class _DevicePtr:
+    """Raw device memory seen through __cuda_array_interface__ (lets torch alias it without owning it)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _as_tensor(ptr: int, nbytes: int, device):
+    import torch
+    return torch.as_tensor(_DevicePtr(ptr, nbytes), device=device)
+
+
+def peer_alloc(nbytes: int, device=None):
+    """(uint8 CUDA tensor over a peer-readable block on the current device, 64-byte handle, raw pointer)."""
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ptr = ctypes.c_void_p()
+    handle = ctypes.create_string_buffer(PEER_HANDLE_BYTES)
+    with torch.cuda.device(dev):
+        check(lib().flash_attn_peer_alloc(nbytes, ctypes.byref(ptr), handle))
+    return _as_tensor(ptr.value, nbytes, dev), handle.raw, ptr.value
+
+
+def peer_open(handle: bytes) -> int:
+    """Map another process's block (same node) into this process; returns the device pointer."""
+    ptr = ctypes.c_void_p()
+    check(lib().flash_attn_peer_open(handle, ctypes.byref(ptr)))
+    return ptr.value
+
+
+def peer_close(ptr: int) -> None:
+    check(lib().flash_attn_peer_close(ptr))
+
+
+def peer_free(ptr: int) -> None:
+    check(lib().flash_attn_peer_free(ptr))
+
+
+def peer_copy(dst_ptr: int, src_ptr: int, nbytes: int, stream=None) -> None:
+    """Enqueue a copy-engine transfer (any mix of local and mapped peer pointers) on a torch stream."""
+    check(lib().flash_attn_peer_copy(dst_ptr, src_ptr, nbytes, _stream_ptr(stream)))
 
 
 def launch_count() -> int:

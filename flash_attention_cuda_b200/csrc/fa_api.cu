@@ -450,6 +450,42 @@ int flash_attn_set_sm_margin(int sms) {
     return g_sm_margin.exchange(sms, std::memory_order_relaxed);
 }
 
+// ---- peer-readable blocks (include/flash_attn.h): cudaMalloc + legacy CUDA IPC.  cudaMalloc rather than a
+// caller-provided pointer: a handle of a sub-allocation of somebody's caching allocator would expose the whole
+// segment, and cuMemMap-based ("expandable") segments cannot be exported this way at all.
+int flash_attn_peer_alloc(size_t bytes, void** ptr, unsigned char* handle) {
+    if (!ptr || !handle) return FA_ERR_NULL_PTR;
+    if (bytes == 0) return FA_ERR_BAD_SHAPE;
+    static_assert(sizeof(cudaIpcMemHandle_t) == FA_PEER_HANDLE_BYTES, "handle size");
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return (int)e;
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, d);
+    if (e != cudaSuccess) { cudaFree(d); return (int)e; }
+    memcpy(handle, &h, sizeof h);
+    *ptr = d;
+    return FA_OK;
+}
+
+int flash_attn_peer_open(const unsigned char* handle, void** ptr) {
+    if (!ptr || !handle) return FA_ERR_NULL_PTR;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    // maps the owner's allocation into this process and enables peer access to the owner's device
+    return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+int flash_attn_peer_close(void* ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : FA_ERR_NULL_PTR; }
+int flash_attn_peer_free(void* ptr) { return ptr ? (int)cudaFree(ptr) : FA_ERR_NULL_PTR; }
+
+int flash_attn_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+    if (!dst || !src) return FA_ERR_NULL_PTR;
+    if (bytes == 0) return FA_OK;
+    // unified addressing: the runtime sees that src lives on another device and programs a copy engine
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+}
+
 unsigned long long flash_attn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void flash_attn_destroy(void) {

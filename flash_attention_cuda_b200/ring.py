@@ -2,10 +2,19 @@
 
 * batch x heads sharding (config 3): every (b, h) is an independent problem (reference
   flash_attention.cu:120-122), so ranks take contiguous slices of B*H and never communicate.
-* ring context parallelism (config 5): the sequence is cut into 2P chunks, rank r owns chunks r and
+* context parallelism (config 5): the sequence is cut into 2P chunks, rank r owns chunks r and
   2P-1-r (zig-zag: every hop costs every rank exactly two unmasked chunk pairs under a causal mask);
-  Q and the partial state stay, K/V chunk pairs travel around the ring with send/recv on a side
-  stream while the current pair is being consumed.  Per-hop math is `flash_attn_fwd_ex`: every chunk
+  Q and the partial state stay.  Two ways of getting at the other ranks' K/V:
+    - exchange="pull" (default on CUDA): nothing travels around a ring.  Every rank keeps its K/V chunk
+      pair in peer-readable memory (`PeerKV`, flash_attn_peer_* in include/flash_attn.h); at hop h a rank
+      pulls the chunks of rank r-h it needs -- only the unmasked ones -- straight out of the owner's HBM
+      with a copy engine over NVLink/NVSwitch, into one of two local landing buffers, while the kernels
+      of hop h-1 run.  No communication kernel competes with the persistent attention grid for SMs, and
+      the ranks are not chained to each other: two tiny all-reduces per step (everyone's K/V in place /
+      everyone done reading) are the only collectives.
+    - exchange="sendrecv": K/V chunk pairs rotate with NCCL send/recv on a side stream (also the path
+      the gloo CPU test runs); needs `flash_attn_set_sm_margin` so that NCCL's kernel finds a free SM.
+  Per-hop math is `flash_attn_fwd_ex`: every chunk
   pair writes its own partial state (O un-normalised fp32, m, l) in the format of the reference's
   split-K code (flash_attention.cu:460-496), and `flash_attn_merge` -- the reference's
   flash_attention_splitk_merge, flash_attention.cu:559-598 -- combines them into O at the end.  (A
@@ -66,40 +75,233 @@ def _cuda_finalize(o_partials, mls, out):
     flash_attn_merge(o_partials, mls, out)
 
 
+def pull_plan(rank: int, world: int, causal: bool) -> List[Tuple[int, List[int], List[Tuple[int, int, bool]]]]:
+    """Hop by hop: (owner rank of the K/V used, K/V chunk slots that must be fetched from it, chunk pairs to
+    compute).  Hop h uses rank (r - h) mod P, so at every hop the ranks read from P distinct owners: each
+    NVSwitch port carries one outgoing and one incoming block.  Under a causal mask an owner ahead of us
+    contributes only its low chunk (its high chunk is entirely in our future) -- half the bytes."""
+    plan = []
+    for hop in range(world):
+        src = (rank - hop) % world
+        pairs = hop_pairs(rank, src, world, causal)
+        plan.append((src, sorted({ki for _, ki, _ in pairs}), pairs))
+    return plan
+
+
+class PeerKV:
+    """This rank's K/V chunk pair in peer-readable device memory, the mapped blocks of all other ranks, and
+    two local landing buffers.  Block layout: [k_lo, k_hi, v_lo, v_hi], each [B, H, C, D] fp16.
+
+    Collective constructor (exchanges the 64-byte handles with all_gather_object).  `self.k` / `self.v` are
+    ordinary torch views of the block: a caller that produces K/V directly into them pays no staging copy.
+    """
+
+    def __init__(self, B: int, H: int, C: int, D: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import peer_alloc, peer_open
+        self.group, self.dev = group, torch.device(device)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.shape = (B, H, C, D)
+        self.chunk_bytes = B * H * C * D * 2
+        self.block, handle, self.ptr = peer_alloc(4 * self.chunk_bytes, self.dev)
+        t = self.block.view(torch.float16).view(4, B, H, C, D)
+        self.k, self.v = [t[0], t[1]], [t[2], t[3]]
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        self.peer_ptr = [self.ptr if r == self.rank else peer_open(handles[r]) for r in range(self.world)]
+        self.land = [torch.empty((4, B, H, C, D), dtype=torch.float16, device=self.dev) for _ in range(2)]
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.comm = torch.cuda.Stream(device=self.dev)
+        self.ready = {}       # hop -> event: landing buffer filled
+        self.consumed = {}    # hop -> event: the kernels reading that hop's buffer have been enqueued
+
+    # -- the five steps the driver calls (tests inject an object with the same methods) --
+    def begin(self, k, v):
+        """Make this rank's K/V readable (staging copy unless the caller already wrote into self.k / self.v),
+        then: everyone's block is in place."""
+        import torch
+        import torch.distributed as dist
+        for mine, given in zip(self.k + self.v, list(k) + list(v)):
+            if mine.data_ptr() != given.data_ptr():
+                mine.copy_(given)
+        dist.all_reduce(self.flag, group=self.group)          # stream-ordered behind the copies above
+        self.comm.wait_stream(torch.cuda.current_stream(self.dev))
+        self.ready.clear()
+        self.consumed.clear()
+        return self.k + self.v
+
+    def prefetch(self, hop: int, src: int, slots):
+        """Start pulling the chunks `slots` of rank `src` for hop `hop` (>= 1) into landing buffer (hop-1)&1."""
+        import torch
+        from . import peer_copy
+        land = self.land[(hop - 1) & 1]
+        if hop - 2 in self.consumed:                          # that buffer's previous readers (hop - 2)
+            self.comm.wait_event(self.consumed[hop - 2])
+        cb = self.chunk_bytes
+        if list(slots) == [0, 1]:
+            spans = [(0, 4)]                                  # the whole block in one transfer
+        else:
+            spans = [(s, 1) for s in slots] + [(2 + s, 1) for s in slots]
+        for first, n in spans:
+            peer_copy(land.data_ptr() + first * cb, self.peer_ptr[src] + first * cb, n * cb, self.comm)
+        ev = torch.cuda.Event()
+        ev.record(self.comm)
+        self.ready[hop] = ev
+
+    def wait(self, hop: int):
+        import torch
+        torch.cuda.current_stream(self.dev).wait_event(self.ready[hop])
+        land = self.land[(hop - 1) & 1]
+        return [land[0], land[1], land[2], land[3]]
+
+    def done(self, hop: int):
+        import torch
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.consumed[hop] = ev
+
+    def end(self):
+        """Everyone is done reading everyone's block: K/V may be rewritten after this (stream-ordered)."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.current_stream(self.dev).wait_stream(self.comm)
+        dist.all_reduce(self.flag, group=self.group)
+
+    def close(self):
+        """Collective: unmap the peers' blocks, then free ours."""
+        import torch
+        import torch.distributed as dist
+        from . import peer_close, peer_free
+        torch.cuda.synchronize(self.dev)
+        for r, ptr in enumerate(self.peer_ptr):
+            if r != self.rank:
+                peer_close(ptr)
+        dist.barrier(group=self.group)                        # nobody still maps our block
+        self.k = self.v = self.block = None
+        peer_free(self.ptr)
+
+
+_peer_kv: dict = {}
+
+
+def peer_kv(B: int, H: int, C: int, D: int, device, group=None) -> PeerKV:
+    """The cached PeerKV for this shape (collective on first use; one shape at a time)."""
+    import torch
+    key = (str(torch.device(device)), B, H, C, D, id(group))
+    px = _peer_kv.get(key)
+    if px is None:
+        release_peer_kv()
+        px = _peer_kv[key] = PeerKV(B, H, C, D, device, group)
+    return px
+
+
+def release_peer_kv() -> None:
+    """Collective: drop the cached PeerKV (call before destroying the process group)."""
+    for px in _peer_kv.values():
+        px.close()
+    _peer_kv.clear()
+
+
+def _partial_workspace(q, world, causal, schedule):
+    """Partial states (one per chunk pair, write-only), cached per (device, shape): a step allocates nothing
+    and zero-fills nothing."""
+    import torch
+    B, H, C, D = q[0].shape
+    dev = q[0].device
+    n_split = [max(1, sum(1 for hp in schedule for (qi, _, _) in hp if qi == i)) for i in range(2)]
+    key = (str(dev), B, H, C, D, q[0].dtype, world, bool(causal), tuple(n_split))
+    ws = _workspace.get(key)
+    if ws is None:
+        ws = {
+            "o_part": [torch.empty((n_split[i], B * H * C, D), dtype=torch.float32, device=dev) for i in range(2)],
+            "ml": [torch.empty((n_split[i], B * H * C, 2), dtype=torch.float32, device=dev) for i in range(2)],
+        }
+        _workspace.clear()          # one shape at a time: the buffers are large
+        _workspace[key] = ws
+    return ws
+
+
+def _merge_partials(q, o_part, ml, used, finalize):
+    import torch
+    out = [torch.empty_like(q[0]), torch.empty_like(q[1])]
+    for i in range(2):
+        if used[i] == 0:           # a Q chunk that saw no key at all (cannot happen with the zig-zag layout)
+            out[i].zero_()
+        else:
+            finalize(o_part[i][:used[i]], ml[i][:used[i]], out[i])
+    return out
+
+
+def pull_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, group=None, *,
+                           partial: Optional[Callable] = None, finalize: Optional[Callable] = None,
+                           peer=None, rank: Optional[int] = None, world: Optional[int] = None):
+    """Context-parallel forward with peer pulls (module docstring).  Same arguments and result as
+    `ring_attention_forward`.  `peer` is a PeerKV (default: the cached one for this shape); tests inject an
+    object with the same begin / prefetch / wait / done / end methods together with rank and world."""
+    partial = partial or _cuda_partial
+    finalize = finalize or _cuda_finalize
+    if rank is None or world is None:
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    B, H, C, D = q[0].shape
+    if peer is None:
+        peer = peer_kv(B, H, C, D, q[0].device, group)
+    plan = pull_plan(rank, world, causal)
+    ws = _partial_workspace(q, world, causal, [pairs for _, _, pairs in plan])
+    o_part, ml = ws["o_part"], ws["ml"]
+    used = [0, 0]
+    qa = zigzag_chunks(rank, world)
+
+    cur = peer.begin(k, v)
+    for hop, (src, _, pairs) in enumerate(plan):
+        if hop + 1 < world:
+            nsrc, nslots, _ = plan[hop + 1]
+            peer.prefetch(hop + 1, nsrc, nslots)       # lands while this hop's kernels run
+        if hop > 0:
+            cur = peer.wait(hop)
+        kb = zigzag_chunks(src, world)
+        for qi, ki, diag in pairs:
+            partial(q[qi], cur[ki], cur[2 + ki], o_part[qi][used[qi]], ml[qi][used[qi]], bool(diag),
+                    qa[qi] * C, kb[ki] * C, False)
+            used[qi] += 1
+        peer.done(hop)
+    peer.end()
+    return _merge_partials(q, o_part, ml, used, finalize)
+
+
 def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, group=None, *,
                            partial: Optional[Callable] = None, finalize: Optional[Callable] = None,
-                           comm_stream=None):
-    """Ring-CP forward.  q, k, v: pairs (low chunk, high chunk) of contiguous [B, H, C, D] tensors in the
-    zig-zag layout of `zigzag_chunks`.  Returns the pair of output chunks, same layout as q.
+                           comm_stream=None, exchange: Optional[str] = None):
+    """Context-parallel forward.  q, k, v: pairs (low chunk, high chunk) of contiguous [B, H, C, D] tensors in
+    the zig-zag layout of `zigzag_chunks`.  Returns the pair of output chunks, same layout as q.
 
-    Each hop: post isend/irecv of the K/V pair for the next hop, run the (at most four, causal: two)
+    exchange = "pull" (CUDA default; FLASH_ATTN_RING_EXCHANGE overrides) or "sendrecv" (module docstring).
+    sendrecv, each hop: post isend/irecv of the K/V pair for the next hop, run the (at most four, causal: two)
     chunk-pair kernels of this hop, wait for the transfer, swap buffers."""
+    import os
     import torch
     import torch.distributed as dist
 
-    partial = partial or _cuda_partial
-    finalize = finalize or _cuda_finalize
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    if exchange is None:
+        exchange = os.environ.get("FLASH_ATTN_RING_EXCHANGE") or ("pull" if q[0].is_cuda and world > 1 else "sendrecv")
+    if exchange not in ("pull", "sendrecv"):
+        raise ValueError(f"exchange must be 'pull' or 'sendrecv', not {exchange!r}")
+    if exchange == "pull":
+        return pull_attention_forward(q, k, v, causal, group, partial=partial, finalize=finalize)
+    partial = partial or _cuda_partial
+    finalize = finalize or _cuda_finalize
     B, H, C, D = q[0].shape
     dev = q[0].device
     on_cuda = dev.type == "cuda"
 
     # Which chunk pairs does this rank compute, hop by hop?  (deterministic: every rank can enumerate it)
     schedule = [hop_pairs(rank, (rank - hop) % world, world, causal) for hop in range(world)]
-    n_split = [max(1, sum(1 for hp in schedule for (qi, _, _) in hp if qi == i)) for i in range(2)]
-    # partial states (one per chunk pair, write-only) and receive buffers are cached per (device, shape):
-    # a ring step allocates nothing and zero-fills nothing
-    key = (str(dev), B, H, C, D, q[0].dtype, world, bool(causal))
-    ws = _workspace.get(key)
-    if ws is None:
-        ws = {
-            "o_part": [torch.empty((n_split[i], B * H * C, D), dtype=torch.float32, device=dev) for i in range(2)],
-            "ml": [torch.empty((n_split[i], B * H * C, 2), dtype=torch.float32, device=dev) for i in range(2)],
-            "recv": [[torch.empty_like(k[0]) for _ in range(4)] for _ in range(2)] if world > 1 else None,
-        }
-        _workspace.clear()          # one shape at a time: the buffers are large
-        _workspace[key] = ws
+    ws = _partial_workspace(q, world, causal, schedule)
+    if world > 1 and "recv" not in ws:     # two receive sets, cached with the partial states
+        ws["recv"] = [[torch.empty_like(k[0]) for _ in range(4)] for _ in range(2)]
     o_part, ml = ws["o_part"], ws["ml"]
     used = [0, 0]          # partial states written so far, per Q chunk
 
@@ -146,10 +348,4 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
     if old_margin is not None:
         from . import set_sm_margin
         set_sm_margin(old_margin)
-    out = [torch.empty_like(q[0]), torch.empty_like(q[1])]
-    for i in range(2):
-        if used[i] == 0:           # a Q chunk that saw no key at all (cannot happen with the zig-zag layout)
-            out[i].zero_()
-        else:
-            finalize(o_part[i][:used[i]], ml[i][:used[i]], out[i])
-    return out
+    return _merge_partials(q, o_part, ml, used, finalize)

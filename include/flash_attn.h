@@ -93,6 +93,21 @@ int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_att
  * previous value; 0 (default) uses the whole device. */
 int flash_attn_set_sm_margin(int sms);
 
+/* Peer-readable K/V blocks: context parallelism without a communication kernel.
+ * With one process per GPU behind NVSwitch every rank can read every other rank's HBM, so the K/V
+ * blocks of a long sequence never have to travel around a ring of send/recv kernels: each rank keeps
+ * its block where it is, in memory obtained from flash_attn_peer_alloc, publishes the 64-byte handle,
+ * and the others map it (flash_attn_peer_open) and PULL the block they need next with a copy engine
+ * (flash_attn_peer_copy = one DMA over NVLink, no SM, no shared memory) while the persistent attention
+ * grid keeps all 148 SMs.  `handle` is a cudaIpcMemHandle_t; it is valid in other processes of the
+ * same node only.  peer_close unmaps an opened block, peer_free releases an allocated one. */
+#define FA_PEER_HANDLE_BYTES 64
+int flash_attn_peer_alloc(size_t bytes, void** ptr, unsigned char* handle);
+int flash_attn_peer_open(const unsigned char* handle, void** ptr);
+int flash_attn_peer_close(void* ptr);
+int flash_attn_peer_free(void* ptr);
+int flash_attn_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+
 /* Number of kernels this library has launched in the calling process (all threads). */
 unsigned long long flash_attn_launch_count(void);
 

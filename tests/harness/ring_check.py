@@ -1,7 +1,7 @@
 """Multi-GPU numerical check of ring context parallelism (run under torchrun on >= 2 GPUs):
 the ring result must equal the monolithic single-kernel result on the same global tensors, and both are
 spot-checked against the CPU oracle on sampled rows.
-   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/harness/ring_check.py [N]"""
+   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/harness/ring_check.py [N] [pull,sendrecv]"""
 import os
 import sys
 
@@ -25,12 +25,13 @@ g = torch.Generator(device="cuda").manual_seed(99)          # identical global t
 q, k = (torch.randn((B, H, N, D), device="cuda", generator=g).half() for _ in range(2))
 v = (torch.randn((B, H, N, D), device="cuda", generator=g) * 0.5).half()
 ok = True
-for causal in (True, False):
+EXCHANGES = sys.argv[2].split(",") if len(sys.argv) > 2 else ["pull", "sendrecv"]
+for causal, exchange in [(c, e) for e in EXCHANGES for c in (True, False)]:
     full = fa.flash_attn_fwd(q, k, v, causal=causal)
     C = N // (2 * world)
     lo, hi = ring.zigzag_chunks(rank, world)
     ch = lambda x: [x[:, :, c * C:(c + 1) * C].contiguous() for c in (lo, hi)]
-    out = ring.ring_attention_forward(ch(q), ch(k), ch(v), causal)
+    out = ring.ring_attention_forward(ch(q), ch(k), ch(v), causal, exchange=exchange)
     torch.cuda.synchronize()
     worst = 0.0
     for o, c in zip(out, (lo, hi)):
@@ -44,9 +45,10 @@ for causal in (True, False):
     mx, mean = _oracle.diff(got, ref)
     good = worst <= 2e-3 and mx <= 2e-3 and mean <= 2e-4
     ok &= good
-    print(f"rank {rank} causal={causal}: ring vs monolithic max|diff|={worst:.2e}; ring vs oracle rows max={mx:.2e} mean={mean:.2e} "
+    print(f"rank {rank} causal={causal} {exchange}: ring vs monolithic max|diff|={worst:.2e}; ring vs oracle rows max={mx:.2e} mean={mean:.2e} "
           f"{'PASS' if good else 'FAIL'}", flush=True)
 t = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(t)
+ring.release_peer_kv()
 dist.destroy_process_group()
 sys.exit(int(t.item() != 0))

@@ -324,3 +324,52 @@ def test_experimental_pair_kernel_passes_the_same_parity_tests(fa):
                        env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+# ---- peer-readable blocks (flash_attn_peer_*): another process maps this process's block and pulls it ----
+_PEER_CHILD = r'''
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+import flash_attention_cuda_b200 as fa
+torch.cuda.set_device(0)
+n = int(sys.argv[3])
+ptr = fa.peer_open(bytes.fromhex(sys.argv[2]))
+dst = torch.zeros(n, dtype=torch.uint8, device="cuda")
+fa.peer_copy(dst.data_ptr(), ptr, n)
+torch.cuda.synchronize()
+print(int(dst.to(torch.int64).sum().item()), int(dst[12345].item()))
+fa.peer_close(ptr)
+'''
+
+
+def test_peer_block_is_readable_from_another_process(fa):
+    import subprocess
+    import sys
+    n = 1 << 20
+    block, handle, ptr = fa.peer_alloc(n)
+    assert block.is_cuda and block.numel() == n and block.data_ptr() == ptr and len(handle) == fa.PEER_HANDLE_BYTES
+    pattern = (torch.arange(n, device="cuda") * 7 % 251).to(torch.uint8)
+    block.copy_(pattern)
+    torch.cuda.synchronize()
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _PEER_CHILD, repo, handle.hex(), str(n)], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    total, probe = (int(x) for x in r.stdout.split())
+    assert total == int(pattern.to(torch.int64).sum().item()) and probe == int(pattern[12345].item())
+    del block
+    fa.peer_free(ptr)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (peer pulls over NVLink)")
+def test_context_parallel_pull_two_gpus_matches_monolithic():
+    """tests/harness/ring_check.py under torchrun: pull and sendrecv exchanges, causal and full, against the
+    monolithic kernel and oracle rows."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(here, "harness", "ring_check.py"), "2048"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("PASS") == 8 and "FAIL" not in r.stdout

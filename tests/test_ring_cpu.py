@@ -142,3 +142,91 @@ def test_bh_shard_partitions_heads():
             assert s == pos
             pos += c
         assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+class FakePeer:
+    """Stand-in for ring.PeerKV: `blocks` plays the peer-readable memory of all ranks.  A pull copies ONLY the
+    requested chunks; the rest of the landing buffer is NaN, so a kernel reading a chunk the plan did not
+    fetch poisons the output.  Also checks the call protocol (prefetch one hop ahead, double buffer)."""
+
+    def __init__(self, blocks, rank):
+        self.blocks, self.rank = blocks, rank
+        self.land = [None, None]
+        self.land_hop = [None, None]
+        self.finished = set()
+        self.log = []
+
+    def begin(self, k, v):
+        assert [t.data_ptr() for t in self.blocks[self.rank]] == [t.data_ptr() for t in list(k) + list(v)]
+        self.log.append("begin")
+        return list(k) + list(v)
+
+    def prefetch(self, hop, src, slots):
+        b = (hop - 1) & 1
+        # the buffer's previous readers (hop - 2) must have been enqueued before it is overwritten
+        assert self.land_hop[b] is None or self.land_hop[b] in self.finished
+        full = [torch.full_like(t, float("nan")) for t in self.blocks[src]]
+        for s in slots:
+            full[s] = self.blocks[src][s].clone()
+            full[2 + s] = self.blocks[src][2 + s].clone()
+        self.land[b], self.land_hop[b] = full, hop
+        self.log.append(("prefetch", hop, src, tuple(slots)))
+
+    def wait(self, hop):
+        b = (hop - 1) & 1
+        assert self.land_hop[b] == hop
+        return self.land[b]
+
+    def done(self, hop):
+        self.finished.add(hop)
+
+    def end(self):
+        self.log.append("end")
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("causal", [True, False])
+def test_pull_cp_all_ranks_simulated(world, causal):
+    """The pull driver has no rank-to-rank dependency inside a step, so all ranks can be run one after the
+    other in one process against a shared table of K/V blocks."""
+    N, D, H = 64 * world, 64, 2
+    rng = np.random.default_rng(11)
+    q, k, v = (rng.standard_normal((1, H, N, D), dtype=np.float32).astype(np.float16) for _ in range(3))
+    v = (v.astype(np.float32) * 0.5).astype(np.float16)
+    C = N // (2 * world)
+
+    def chunks(x, rank):
+        t = torch.from_numpy(x)
+        return [t[:, :, c * C:(c + 1) * C].contiguous() for c in ring.zigzag_chunks(rank, world)]
+
+    blocks = {r: chunks(k, r) + chunks(v, r) for r in range(world)}
+    ref = _oracle.attention(q, k, v, causal)
+    for rank in range(world):
+        peer = FakePeer(blocks, rank)
+        out = ring.pull_attention_forward(chunks(q, rank), blocks[rank][:2], blocks[rank][2:], causal,
+                                          partial=np_partial, finalize=np_finalize, peer=peer, rank=rank, world=world)
+        assert peer.log[0] == "begin" and peer.log[-1] == "end"
+        assert [e[1] for e in peer.log[1:-1]] == list(range(1, world))
+        for o, c in zip(out, ring.zigzag_chunks(rank, world)):
+            mx, mean = _oracle.diff(o.numpy(), ref[:, :, c * C:(c + 1) * C])
+            assert mx <= 2e-3 and mean <= 2e-4, (rank, c, mx, mean)
+
+
+def test_pull_plan_reads_distinct_owners_and_skips_masked_chunks():
+    for world in (2, 4, 8):
+        plans = [ring.pull_plan(r, world, True) for r in range(world)]
+        for hop in range(world):
+            # one reader per owner at every hop: no NVSwitch port is asked for two blocks at once
+            assert sorted(plans[r][hop][0] for r in range(world)) == list(range(world))
+        for r in range(world):
+            fetched = 0
+            for hop, (src, slots, pairs) in enumerate(plans[r]):
+                assert src == (r - hop) % world
+                assert set(slots) == {ki for _, ki, _ in pairs}
+                if hop:
+                    fetched += len(slots)
+                    # an owner ahead of us in the sequence contributes its low chunk only
+                    assert slots == ([0] if src < r else [0, 1])
+            assert fetched == r + 2 * (world - 1 - r)
+        full = ring.pull_plan(0, world, False)
+        assert all(slots == [0, 1] and len(pairs) == 4 for _, slots, pairs in full)
