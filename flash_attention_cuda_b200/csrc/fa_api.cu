@@ -20,6 +20,7 @@ namespace {
 constexpr int kMaxDevices = 64;
 constexpr int kSchedSlots = 4096;
 constexpr int kHostChunks = 8;     // head chunks flash_attn_fwd_host pipelines over PCIe
+constexpr int kGroupMB = 32;       // K+V bytes of one scheduling group of heads (make_params)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -158,11 +159,20 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     p.nqp = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
     const long long tw = (long long)BH * p.nqp;
     p.total_work = (int)tw;
-    // heads per scheduling group: K+V of the group <= 64 MB (half of B200's 126 MB L2)
+    // heads per scheduling group: K+V of the group <= kGroupMB (B200's 126 MB L2 is two 63 MB halves, and a line
+    // read from the far half is also kept in the near one); FLASH_ATTN_B200_L2_GROUP_MB overrides for A/B runs
+    static const long long group_mb = [] {
+        const char* e = getenv("FLASH_ATTN_B200_L2_GROUP_MB");
+        const long long v = e ? atoll(e) : 0;
+        return v > 0 ? v : (long long)kGroupMB;
+    }();
     const long long kv_bytes = 2LL * Nkv * D * 2;
-    long long gh = (64LL << 20) / (kv_bytes > 0 ? kv_bytes : 1);
+    long long gh = (group_mb << 20) / (kv_bytes > 0 ? kv_bytes : 1);
     if (gh < 1) gh = 1;
     if (gh > BH) gh = BH;
+    // equal groups: a short last group would start its heaviest items when the launch is almost over
+    const long long n_groups = (BH + gh - 1) / gh;
+    gh = (BH + n_groups - 1) / n_groups;
     p.group_heads = (int)gh;
     p.scale = 1.0f / sqrtf((float)D);             // FA.cu:612
     p.scale_log2 = p.scale * 1.4426950408889634f;

@@ -56,8 +56,26 @@ constexpr int kMmaWarp = 8;
 constexpr int kLoadWarp = 9;
 constexpr int kStoreWarp = 10;
 constexpr int kTmemCols = 512;
-constexpr int kRegsSoftmax = 208;   // setmaxnreg: softmax warpgroups grow, the producer/MMA warpgroup shrinks
-constexpr int kRegsOther = 80;      // 2*128*208 + 128*80 = 63488 <= 168 (launch) * 384
+#ifndef FA_REGS_SOFTMAX
+#define FA_REGS_SOFTMAX 208
+#endif
+#ifndef FA_REGS_OTHER
+#define FA_REGS_OTHER 80
+#endif
+constexpr int kRegsSoftmax = FA_REGS_SOFTMAX;   // setmaxnreg: softmax warpgroups grow, the producer/MMA warpgroup shrinks
+constexpr int kRegsOther = FA_REGS_OTHER;       // 2*128*208 + 128*80 = 63488 <= 168 (launch) * 384
+static_assert(2 * 128 * kRegsSoftmax + 128 * kRegsOther <= 65536, "register file");
+// P_t reaches the MMA warp in kPParts pieces (k-steps of 16 keys: [0,4) [4,8) or [0,4) [4,6) [6,8)): the PV k-steps of
+// a piece run under the exponentials of the next one, and only the last piece's k-steps sit between the end of the
+// softmax and the next QK^T of the tile.
+#ifndef FA_P_PARTS
+#define FA_P_PARTS 2
+#endif
+constexpr int kPParts = FA_P_PARTS;
+static_assert(kPParts == 2 || kPParts == 3, "P is delivered in 2 or 3 pieces");
+__host__ __device__ constexpr int p_part_ks(int part) {   // first k-step of a piece
+    return kPParts == 2 ? part * 4 : (part == 0 ? 0 : part == 1 ? 4 : part == 2 ? 6 : 8);
+}
 constexpr float kRescaleThreshold = 8.0f;   // lazy rescale: tolerate P up to 2^8 before moving the reference max
 // Of every 4 element pairs, this many take exp2 on the FMA pipe (Cody-Waite + degree-3 minimax)
 // instead of MUFU.EX2: at 16 MUFU/clk/SM the 16384 exponentials of a 128x128 tile cost as many
@@ -82,7 +100,7 @@ struct Cfg {
     static constexpr int kSmemQ = 4 * kTileBytes;
     static constexpr int kSmemKV = kStages * kTileBytes;
     static constexpr int kBarOffset = kSmemQ + kSmemKV;
-    static constexpr int kNumBars = 4 + 2 * kStages + 8 + 4 + 4;
+    static constexpr int kNumBars = 4 + 2 * kStages + 12 + 4 + 4;
     static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 32 + 1024;  // +32: tmem slot, scheduler slots; +1024: manual alignment slack
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
     static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
@@ -188,12 +206,12 @@ __device__ __forceinline__ void exp2_pair(uint64_t x2, float& p0, float& p1) {
     }
 }
 
-// exponentials + fp16 packing of 64 consecutive columns (one half of the tile)
-template <int kPoly>
+// exponentials + fp16 packing of kCols consecutive columns (64 = one half of the tile)
+template <int kPoly, int kCols = 64>
 __device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64_t scale2, uint64_t neg2,
                                          uint64_t& sum_a, uint64_t& sum_b) {
 #pragma unroll
-    for (int i = 0; i < 64; i += 8) {
+    for (int i = 0; i < kCols; i += 8) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int e = i + 2 * q;
@@ -282,16 +300,32 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     const uint64_t neg2 = pack_f32x2(neg, neg);
     uint64_t sum_a = 0ull, sum_b = 0ull;     // (0.f, 0.f)
     uint32_t pk[32];
-    // P_t (fp16 A operand of PV) overwrites columns [0,64) of S_t, delivered in two halves:
-    // keys 0-63 -> columns [0,32) -> barrier half 0, keys 64-127 -> columns [32,64) -> half 1
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        exp_half<kPoly>(s + 64 * h, pk, scale2, neg2, sum_a, sum_b);
-        tmem_st_x32(tS + 32 * h, pk);
+    // P_t (fp16 A operand of PV) overwrites columns [0,64) of S_t (key c -> column c/2), delivered in kPParts pieces:
+    // keys 0-63 -> piece 0, keys 64-127 -> piece 1 (or 64-95 -> piece 1, 96-127 -> piece 2)
+    // The wait::st + arrive of a piece are issued under the exponentials of the next piece (the store's latency
+    // would otherwise sit on this thread's critical path: +1-3 % at N <= 2048, profiles/r01_v4b_defer_group_ab.log).
+    auto publish = [&](int part) {
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane_id() == 0) mbar_arrive(bar_p_full + 8 * h);   // one arrival per warp (barrier count 4)
+        if (lane_id() == 0) mbar_arrive(bar_p_full + 8 * part);   // one arrival per warp (barrier count 4)
+    };
+    uint32_t pk2[32];
+    exp_half<kPoly>(s, pk, scale2, neg2, sum_a, sum_b);
+    tmem_st_x32(tS, pk);
+    exp_half<kPoly, 32>(s + 64, pk2, scale2, neg2, sum_a, sum_b);
+    publish(0);
+    if (kPParts == 2) {
+        exp_half<kPoly, 32>(s + 96, pk2 + 16, scale2, neg2, sum_a, sum_b);
+        tmem_st_x32(tS + 32, pk2);
+        publish(1);
+    } else {
+        tmem_st_x16(tS + 32, pk2);
+        exp_half<kPoly, 16>(s + 96, pk2 + 16, scale2, neg2, sum_a, sum_b);
+        publish(1);
+        exp_half<kPoly, 16>(s + 112, pk2 + 24, scale2, neg2, sum_a, sum_b);
+        tmem_st_x16(tS + 48, pk2 + 16);
+        publish(2);
     }
     float a0, a1;
     unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
@@ -314,8 +348,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t bar_kv_full = bars + 32;                       // [kStages]
     const uint32_t bar_kv_empty = bar_kv_full + 8 * C::kStages;   // [kStages]
     const uint32_t bar_s_full = bar_kv_empty + 8 * C::kStages;    // [tile]
-    const uint32_t bar_p_full = bar_s_full + 16;                  // [tile][half]  index 2*t + h
-    const uint32_t bar_o_full = bar_p_full + 32;                  // [tile]
+    const uint32_t bar_p_full = bar_s_full + 16;                  // [tile][piece]  index 4*t + piece
+    const uint32_t bar_o_full = bar_p_full + 64;                  // [tile]
     const uint32_t bar_o_staged = bar_o_full + 16;                // [Q slot][tile] softmax warps -> store warp
     const uint32_t bar_sched_full = bar_o_staged + 32;            // [2] work-index slots, producer -> everyone
     const uint32_t bar_sched_empty = bar_sched_full + 16;         // [2]
@@ -345,8 +379,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
         for (int t = 0; t < 2; t++) {
             mbar_init(bar_s_full + 8 * t, 1);
-            mbar_init(bar_p_full + 16 * t, 4);        // one arrival per softmax warp of the tile,
-            mbar_init(bar_p_full + 16 * t + 8, 4);    // per half of P
+            for (int part = 0; part < 4; part++)
+                mbar_init(bar_p_full + 32 * t + 8 * part, 4);   // one arrival per softmax warp of the tile, per piece of P
             mbar_init(bar_o_full + 8 * t, 1);
             mbar_init(bar_o_staged + 8 * t, 4);       // one arrival per softmax warp of the tile,
             mbar_init(bar_o_staged + 8 * (2 + t), 4); // per Q slot
@@ -471,20 +505,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             __syncwarp();
         };
         // O_t (+)= P_t V_j : 8 k-steps of 16 kv rows (P k-step = 8 TMEM columns, V k-step = 16 rows * 128 B),
-        // issued in two halves of 4 k-steps as the two halves of P arrive
+        // issued piece by piece as the pieces of P arrive
         auto issue_pv = [&](uint32_t tO, uint32_t tP, uint32_t v_smem, bool accumulate, uint32_t bar_p,
                             uint32_t parity, uint32_t bar_o, int tag) {
             const uint64_t vdesc = umma_smem_desc(v_smem, C::kPanelBytes, 1024);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                mbar_wait(bar_p + 8 * h, parity, tag);
+            for (int part = 0; part < kPParts; part++) {
+                mbar_wait(bar_p + 8 * part, parity, tag);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
-                    for (int ks = 4 * h; ks < 4 * h + 4; ks++)
+                    for (int ks = p_part_ks(part); ks < p_part_ks(part + 1); ks++)
                         umma_ts(tO, tP + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV,
                                 (accumulate || ks > 0) ? 1u : 0u);
-                    if (h == 1) umma_commit(bar_o);
+                    if (part == kPParts - 1) umma_commit(bar_o);
                 }
                 __syncwarp();
             }
@@ -543,7 +577,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 if (j + 1 < n0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
                 // ---- tile 1: PV1(j), QK1(j+1)
                 if (j < n1) {
-                    issue_pv(tO1, tS1, v_smem, j > 0, bar_p_full + 16, p_phase1, bar_o_full + 8, 14);
+                    issue_pv(tO1, tS1, v_smem, j > 0, bar_p_full + 32, p_phase1, bar_o_full + 8, 14);
                     p_phase1 ^= 1u;
                 }
                 commit(bar_kv_empty + 8 * rv.idx);
@@ -604,7 +638,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const uint32_t tS = tmem_base + lane_base + (t ? C::kTmemS1 : C::kTmemS0);
         const uint32_t tO = tmem_base + lane_base + (t ? C::kTmemO1 : C::kTmemO0);
         const uint32_t my_s_full = bar_s_full + 8 * t;
-        const uint32_t my_p_full = bar_p_full + 16 * t;        // + 8 * half
+        const uint32_t my_p_full = bar_p_full + 32 * t;        // + 8 * piece
         const uint32_t my_o_full = bar_o_full + 8 * t;
         uint32_t s_phase = 0;
         uint32_t pv_count = 0;   // P tiles handed to the MMA warp so far == o_full completions expected

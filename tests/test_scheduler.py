@@ -42,14 +42,14 @@ def test_every_q_tile_exactly_once(N, causal):
 
 
 def test_heavy_first_within_l2_sized_head_groups():
-    # N=8192 D=128: K+V of a head = 4 MB -> 16 heads per group; inside a group heavy-first across heads
+    # N=8192 D=128: K+V of a head = 4 MB -> 8 heads per 32 MB group; inside a group heavy-first across heads
     its = items(1, 32, 8192, 8192, 128, True)
     nqp = 64 // fa.tiles_per_item(128)
-    per_group = 16 * nqp
+    per_group = 8 * nqp
     assert len(its) == 32 * nqp
-    for g in range(2):
+    for g in range(4):
         grp = its[g * per_group:(g + 1) * per_group]
-        assert {it["bh"] for it in grp} == set(range(16 * g, 16 * g + 16))
+        assert {it["bh"] for it in grp} == set(range(8 * g, 8 * g + 8))
         w = [it["n"] for it in grp]
         assert w == sorted(w, reverse=True)
     # the launch ends with the lightest items
@@ -64,12 +64,12 @@ def test_short_sequences_form_one_group():
 
 
 def test_last_group_may_be_smaller():
-    # 5 heads of 16 MB K/V each (N=32768): groups of 4 + 1, every (head, pair) still exactly once
+    # 5 heads of 16 MB K/V each (N=32768): 32 MB groups of 2 + 2 + 1, every (head, pair) still exactly once
     its = items(1, 5, 32768, 32768, 128, True)
     seen = {(it["bh"], it["q0"]) for it in its}
     units = 256 // fa.tiles_per_item(128)
     assert len(seen) == len(its) == 5 * units
-    assert [it["bh"] for it in its[:4]] == [0, 1, 2, 3] and its[4 * units]["bh"] == 4
+    assert [it["bh"] for it in its[:4]] == [0, 1, 0, 1] and its[2 * units]["bh"] == 2 and its[4 * units]["bh"] == 4
 
 
 def test_masked_tiles_skipped_with_offsets():
@@ -87,3 +87,13 @@ def test_total_causal_tiles_is_triangular():
     tiles = sum(it["n0"] + it["n1"] for it in its)
     n = N // 128
     assert tiles == n * (n + 1) // 2
+
+
+def test_head_groups_are_equal_sized():
+    # 20 heads of 4 MB: 8 per 32 MB group would leave a last group of 4 -> three groups of 7, 7, 6 instead
+    its = items(1, 20, 8192, 8192, 128, True)
+    nqp = 64 // fa.tiles_per_item(128)
+    assert len(its) == 20 * nqp
+    bounds = [0, 7 * nqp, 14 * nqp, 20 * nqp]
+    heads = [sorted({it["bh"] for it in its[a:b]}) for a, b in zip(bounds, bounds[1:])]
+    assert heads == [list(range(0, 7)), list(range(7, 14)), list(range(14, 20))]
