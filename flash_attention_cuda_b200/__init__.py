@@ -34,6 +34,7 @@ ERRORS = {
 # every symbol include/flash_attn.h declares
 EXPORTED_SYMBOLS = (
     "flash_attn_fwd",
+    "flash_attn_fwd_bf16",
     "flash_attn_fwd_ex",
     "flash_attn_finalize",
     "flash_attn_merge",
@@ -94,6 +95,9 @@ def lib() -> ctypes.CDLL:
     vp, ci, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
     L.flash_attn_fwd.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     L.flash_attn_fwd.restype = ci
+    if hasattr(L, "flash_attn_fwd_bf16"):   # absent from archived A/B builds of older kernels
+        L.flash_attn_fwd_bf16.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+        L.flash_attn_fwd_bf16.restype = ci
     L.flash_attn_fwd_ex.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ll, ll, ci, vp]
     L.flash_attn_fwd_ex.restype = ci
     L.flash_attn_finalize.argtypes = [vp, vp, vp, ll, ci, vp]
@@ -148,15 +152,15 @@ def _stream_ptr(stream=None):
 
 
 def flash_attn_fwd(q, k, v, causal: bool = True, out=None, stream=None):
-    """O = softmax(Q K^T / sqrt(D) [+ causal mask]) V for FP16 CUDA tensors [B, H, N, D].
+    """O = softmax(Q K^T / sqrt(D) [+ causal mask]) V for FP16 (or BF16) CUDA tensors [B, H, N, D].
 
     Same contract as the reference dispatcher (flash_attention.cu:606-663); enqueues on the
     current (or given) torch stream and returns the output tensor without synchronising."""
     import torch
     if not (q.is_cuda and k.is_cuda and v.is_cuda):
         raise ValueError("flash_attn_fwd needs CUDA tensors (there is no CPU path)")
-    if q.dtype != torch.float16 or k.dtype != torch.float16 or v.dtype != torch.float16:
-        raise TypeError("flash_attn_fwd takes float16 tensors")
+    if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise TypeError("flash_attn_fwd takes float16 (or bfloat16) tensors, all of one type")
     if q.dim() != 4 or q.shape != k.shape or q.shape != v.shape:
         raise ValueError("q, k, v must all be [B, H, N, D]")
     if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
@@ -164,9 +168,12 @@ def flash_attn_fwd(q, k, v, causal: bool = True, out=None, stream=None):
     B, H, N, D = q.shape
     if out is None:
         out = torch.empty_like(q)
+    if out.dtype != q.dtype:
+        raise TypeError("out must have the dtype of q, k, v")
+    entry = lib().flash_attn_fwd if q.dtype == torch.float16 else lib().flash_attn_fwd_bf16
     with torch.cuda.device(q.device):
-        rc = lib().flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
-                                  B, H, N, D, 1 if causal else 0, _stream_ptr(stream))
+        rc = entry(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                   B, H, N, D, 1 if causal else 0, _stream_ptr(stream))
     check(rc)
     return out
 

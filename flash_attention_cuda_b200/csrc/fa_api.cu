@@ -60,9 +60,9 @@ void load_encode_fn() {
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
 }
 
-template <int D, int kPoly>
+template <int D, int kPoly, bool kBF16 = false>
 int set_kernel_attrs() {
-    return (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D, kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D, kPoly, kBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      fa::Cfg<D>::kSmemBytes);
 }
 // exp2 on the FMA pipe for 1 pair in 4 only where it pays: D = 128 and at least 32 KV tiles (fa_fwd_sm100.cuh)
@@ -111,6 +111,9 @@ DeviceState* device_state(int* err) {
         int r = set_kernel_attrs<128, 1>();
         if (r == 0) r = set_kernel_attrs<128, 0>();
         if (r == 0) r = set_kernel_attrs<64, 0>();
+        if (r == 0) r = set_kernel_attrs<128, 1, true>();
+        if (r == 0) r = set_kernel_attrs<128, 0, true>();
+        if (r == 0) r = set_kernel_attrs<64, 0, true>();
         if (r == 0 && use_pair_kernel()) {
             r = set_pair_kernel_attrs<128, 1>();
             if (r == 0) r = set_pair_kernel_attrs<128, 2>();
@@ -126,14 +129,14 @@ DeviceState* device_state(int* err) {
 
 // [BH, N, D] fp16, box = 64 halves x `rows` rows x 1 head, 128-byte swizzle; rows past N read as zero
 // (and are dropped on a TMA store).
-int make_tmap(CUtensorMap* tm, const void* base, int BH, int N, int D, int rows = fa::kBlockN) {
+int make_tmap(CUtensorMap* tm, const void* base, int BH, int N, int D, int rows = fa::kBlockN, bool bf16 = false) {
     std::call_once(g_encode_once, load_encode_fn);
     if (!g_encode) return FA_ERR_TENSORMAP;
     cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)BH};
     cuuint64_t gstride[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+    CUresult r = g_encode(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? FA_OK : FA_ERR_TENSORMAP;
@@ -179,7 +182,7 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     return p;
 }
 
-template <int D, int kPoly>
+template <int D, int kPoly, bool kBF16 = false>
 int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
            const CUtensorMap& to, fa::Params p, cudaStream_t stream) {
     int avail = st->num_sms - g_sm_margin.load(std::memory_order_relaxed);
@@ -200,7 +203,7 @@ int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D, kPoly>, tq, tk, tv, to, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D, kPoly, kBF16>, tq, tk, tv, to, p);
     if (le != cudaSuccess) return (int)le;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();   // FA.cu:662
@@ -267,19 +270,24 @@ int run_pair(DeviceState* st, const void* q, const void* k, const void* v, const
                      : launch_pair<128, 1>(st, tq, tk, tv, to, p, stream);
 }
 
-int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaStream_t stream) {
+int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaStream_t stream, bool bf16 = false) {
     int err = 0;
     DeviceState* st = device_state(&err);
     if (!st) return err;
-    if (use_pair_kernel()) return run_pair(st, q, k, v, p, D, stream);
+    if (use_pair_kernel() && !bf16) return run_pair(st, q, k, v, p, D, stream);   // the experimental kernel is FP16 only
     if ((long long)p.BH * p.nqp > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
     CUtensorMap tq, tk, tv, to;
     int rc;
-    if ((rc = make_tmap(&tq, q, p.BH, p.Nq, D)) != FA_OK) return rc;
-    if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D)) != FA_OK) return rc;
-    if ((rc = make_tmap(&tv, v, p.BH, p.Nkv, D)) != FA_OK) return rc;
+    if ((rc = make_tmap(&tq, q, p.BH, p.Nq, D, fa::kBlockN, bf16)) != FA_OK) return rc;
+    if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D, fa::kBlockN, bf16)) != FA_OK) return rc;
+    if ((rc = make_tmap(&tv, v, p.BH, p.Nkv, D, fa::kBlockN, bf16)) != FA_OK) return rc;
     // O store map (unused in partial mode: describe Q's extent on a valid pointer)
-    if ((rc = make_tmap(&to, p.o ? (const void*)p.o : q, p.BH, p.Nq, D)) != FA_OK) return rc;
+    if ((rc = make_tmap(&to, p.o ? (const void*)p.o : q, p.BH, p.Nq, D, fa::kBlockN, bf16)) != FA_OK) return rc;
+    if (bf16) {
+        if (D == 64) return launch<64, 0, true>(st, tq, tk, tv, to, p, stream);
+        return use_poly(D, p.Nkv) ? launch<128, 1, true>(st, tq, tk, tv, to, p, stream)
+                                  : launch<128, 0, true>(st, tq, tk, tv, to, p, stream);
+    }
     if (D == 64) return launch<64, 0>(st, tq, tk, tv, to, p, stream);
     return use_poly(D, p.Nkv) ? launch<128, 1>(st, tq, tk, tv, to, p, stream) : launch<128, 0>(st, tq, tk, tv, to, p, stream);
 }
@@ -295,6 +303,15 @@ int flash_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, 
     fa::Params p = make_params(B * H, N, N, D, causal, 0);
     p.o = static_cast<__half*>(o);
     return run(q, k, v, p, D, static_cast<cudaStream_t>(stream));
+}
+
+int flash_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, int B, int H, int N, int D, int causal,
+                        void* stream) {
+    int rc = validate(q, k, v, o, B, H, N, N, D);
+    if (rc != FA_OK) return rc;
+    fa::Params p = make_params(B * H, N, N, D, causal, 0);
+    p.o = static_cast<__half*>(o);       // 16-bit elements either way; the kernel instantiation decides the format
+    return run(q, k, v, p, D, static_cast<cudaStream_t>(stream), /*bf16=*/true);
 }
 
 int flash_attn_fwd_ex(const void* q, const void* k, const void* v, float* o_partial, float* ml, int B, int H,

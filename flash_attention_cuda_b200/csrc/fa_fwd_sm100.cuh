@@ -37,6 +37,7 @@
 // smem port).  N=128 sits exactly at the port limit, so the S->P->PV->QK chain is shortened instead.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <float.h>
@@ -106,10 +107,12 @@ struct Cfg {
     static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
     static constexpr uint32_t kIdescQK = umma_idesc_f16(kBlockM, kBlockN, 0, 0);
     static constexpr uint32_t kIdescPV = umma_idesc_f16(kBlockM, D, 0, 1);  // V is MN-major ([kv][d], d contiguous)
+    // BF16 operands (Q, K, V and therefore P): A and B format fields [7,10) / [10,13) = 1
+    static constexpr uint32_t kBf16Operands = (1u << 7) | (1u << 10);
 };
 
 struct Params {
-    __half* o;          // fp16 output [BH, Nq, D]            (partial_mode == 0)
+    __half* o;          // fp16 (or bf16: kernel template) output [BH, Nq, D]   (partial_mode == 0)
     float* o_partial;   // fp32 un-normalised [BH*Nq, D]       (partial_mode == 1; FA.cu:460-496 format)
     float* ml;          // (m, l) pairs [BH*Nq, 2]
     int Nq, Nkv, BH;
@@ -206,8 +209,19 @@ __device__ __forceinline__ void exp2_pair(uint64_t x2, float& p0, float& p1) {
     }
 }
 
+// two fp32 -> one 32-bit word of the tensors' 16-bit format, round to nearest (low half = first value)
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
+    if (kBF16) {
+        __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&b);
+    }
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // exponentials + fp16 packing of kCols consecutive columns (64 = one half of the tile)
-template <int kPoly, int kCols = 64>
+template <int kPoly, bool kBF16, int kCols = 64>
 __device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64_t scale2, uint64_t neg2,
                                          uint64_t& sum_a, uint64_t& sum_b) {
 #pragma unroll
@@ -226,14 +240,13 @@ __device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64
 #endif
             if (q & 1) sum_b = add_f32x2(sum_b, pack_f32x2(p0, p1));   // row sum of the un-rounded p (FA.cu:273-279)
             else sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
-            __half2 h = __floats2half2_rn(p0, p1);                     // low half = even column
-            pk[e / 2] = *reinterpret_cast<uint32_t*>(&h);
+            pk[e / 2] = pack_16x2<kBF16>(p0, p1);                      // low half = even column
         }
     }
 }
 
 // ---- softmax of one 128x128 S tile; one thread owns one row ----
-template <int D, bool kMask, int kPoly>
+template <int D, bool kMask, int kPoly, bool kBF16>
 __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
                                              uint32_t bar_o_full, int lim_local, bool have_o,
                                              uint32_t pv_count, float& m_ref, float& l_run) {
@@ -311,19 +324,19 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
         if (lane_id() == 0) mbar_arrive(bar_p_full + 8 * part);   // one arrival per warp (barrier count 4)
     };
     uint32_t pk2[32];
-    exp_half<kPoly>(s, pk, scale2, neg2, sum_a, sum_b);
+    exp_half<kPoly, kBF16>(s, pk, scale2, neg2, sum_a, sum_b);
     tmem_st_x32(tS, pk);
-    exp_half<kPoly, 32>(s + 64, pk2, scale2, neg2, sum_a, sum_b);
+    exp_half<kPoly, kBF16, 32>(s + 64, pk2, scale2, neg2, sum_a, sum_b);
     publish(0);
     if (kPParts == 2) {
-        exp_half<kPoly, 32>(s + 96, pk2 + 16, scale2, neg2, sum_a, sum_b);
+        exp_half<kPoly, kBF16, 32>(s + 96, pk2 + 16, scale2, neg2, sum_a, sum_b);
         tmem_st_x32(tS + 32, pk2);
         publish(1);
     } else {
         tmem_st_x16(tS + 32, pk2);
-        exp_half<kPoly, 16>(s + 96, pk2 + 16, scale2, neg2, sum_a, sum_b);
+        exp_half<kPoly, kBF16, 16>(s + 96, pk2 + 16, scale2, neg2, sum_a, sum_b);
         publish(1);
-        exp_half<kPoly, 16>(s + 112, pk2 + 24, scale2, neg2, sum_a, sum_b);
+        exp_half<kPoly, kBF16, 16>(s + 112, pk2 + 24, scale2, neg2, sum_a, sum_b);
         tmem_st_x16(tS + 48, pk2 + 16);
         publish(2);
     }
@@ -332,7 +345,7 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     l_run += a0 + a1;
 }
 
-template <int D, int kPoly>
+template <int D, int kPoly, bool kBF16 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
@@ -498,7 +511,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
                 for (int ks = 0; ks < D / 16; ks++) {
                     const uint64_t off = (uint64_t)(((ks >> 2) * C::kPanelBytes + (ks & 3) * 32) >> 4);
-                    umma_ss(tS, qdesc + off, kdesc + off, C::kIdescQK, ks > 0 ? 1u : 0u);
+                    umma_ss(tS, qdesc + off, kdesc + off, C::kIdescQK | (kBF16 ? C::kBf16Operands : 0u), ks > 0 ? 1u : 0u);
                 }
                 umma_commit(bar);
             }
@@ -516,7 +529,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 if (elect_one()) {
 #pragma unroll
                     for (int ks = p_part_ks(part); ks < p_part_ks(part + 1); ks++)
-                        umma_ts(tO, tP + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV,
+                        umma_ts(tO, tP + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV | (kBF16 ? C::kBf16Operands : 0u),
                                 (accumulate || ks > 0) ? 1u : 0u);
                     if (part == kPParts - 1) umma_commit(bar_o);
                 }
@@ -671,9 +684,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 const int k0 = j * kBlockN;
                 const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
                 if (need_mask)
-                    softmax_tile<D, true, kPoly>(p, tS, tO, my_p_full, my_o_full, lim - k0, j > 0, pv_count, m_ref, l_run);
+                    softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, lim - k0, j > 0, pv_count, m_ref, l_run);
                 else
-                    softmax_tile<D, false, kPoly>(p, tS, tO, my_p_full, my_o_full, kBlockN, j > 0, pv_count, m_ref, l_run);
+                    softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, kBlockN, j > 0, pv_count, m_ref, l_run);
                 ++pv_count;
 #ifdef FA_TIMING
                 if (lane == 0 && (warp & 3) == 0 && j > 0 && (j & 7) == 0) {   // sampled: 1 tile in 8
@@ -711,16 +724,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     for (int i = 0; i < 32; i += 8) {
                         const int col = c + i;
                         const uint32_t addr = stage + (col >> 6) * C::kPanelBytes + ((((col & 63) >> 3) ^ (row_in_tile & 7)) << 4);
-                        __half2 h;
-                        uint32_t v0, v1, v2, v3;
-                        h = __floats2half2_rn(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
-                        v0 = *reinterpret_cast<uint32_t*>(&h);
-                        h = __floats2half2_rn(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-                        v1 = *reinterpret_cast<uint32_t*>(&h);
-                        h = __floats2half2_rn(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-                        v2 = *reinterpret_cast<uint32_t*>(&h);
-                        h = __floats2half2_rn(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-                        v3 = *reinterpret_cast<uint32_t*>(&h);
+                        const uint32_t v0 = pack_16x2<kBF16>(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
+                        const uint32_t v1 = pack_16x2<kBF16>(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                        const uint32_t v2 = pack_16x2<kBF16>(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                        const uint32_t v3 = pack_16x2<kBF16>(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
                         st_shared_v4(addr, v0, v1, v2, v3);
                     }
                 }

@@ -4,7 +4,8 @@ The reference ships no binding and compares itself against "PyTorch FA2" in its 
 this makes the same comparison reproducible on the box -- `F.scaled_dot_product_attention` as one more
 reference point next to the CPU oracle, never as a dispatch target -- and lets the kernel sit inside
 `torch.compile`d graphs (a fake/meta implementation describes the output).  The op is a thin wrapper
-over the C ABI (`flash_attn_fwd`): FP16 CUDA tensors `[B, H, N, D]`, D in {64, 128}, scale 1/sqrt(D).
+over the C ABI (`flash_attn_fwd` / `flash_attn_fwd_bf16`): FP16 or BF16 CUDA tensors `[B, H, N, D]`, D in {64, 128},
+scale 1/sqrt(D).
 There is no CPU implementation: calling it with CPU tensors raises.
 
     import flash_attention_cuda_b200.torch_op            # registers the op
@@ -27,8 +28,8 @@ def _fwd_cuda(q, k, v, causal):
 def _fwd_meta(q, k, v, causal):
     if q.dim() != 4 or q.shape != k.shape or q.shape != v.shape:
         raise ValueError("q, k, v must all be [B, H, N, D]")
-    if q.dtype != torch.float16:
-        raise TypeError("flashattn_b200::fwd takes float16 tensors")
+    if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise TypeError("flashattn_b200::fwd takes float16 or bfloat16 tensors, all of one type")
     if q.shape[-1] not in (64, 128):
         raise ValueError("head_dim must be 64 or 128")
     return torch.empty_like(q, memory_format=torch.contiguous_format)

@@ -42,6 +42,11 @@ extern "C" {
 int flash_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int H, int N, int D,
                    int causal, void* stream);
 
+/* Same operation on BF16 tensors (the reference is FP16 only): Q, K, V and O are bfloat16, the
+ * tensor cores take BF16 operands (P is rounded to BF16 as well), S and O accumulate in FP32. */
+int flash_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, int B, int H, int N, int D,
+                        int causal, void* stream);
+
 /* Extended entry: one K/V block of a longer sequence, for ring context
  * parallelism and split-KV.  Computes attention of the local queries q[B,H,Nq,D] against
  * k/v[B,H,Nkv,D] where the queries sit at global positions q_offset.. and the keys at

@@ -373,3 +373,36 @@ def test_context_parallel_pull_two_gpus_matches_monolithic():
                         os.path.join(here, "harness", "ring_check.py"), "2048"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("PASS") == 8 and "FAIL" not in r.stdout
+
+
+# ---- BF16 operands (flash_attn_fwd_bf16; the reference is FP16 only) ----
+# Gate: the oracle is evaluated on the same values (BF16 inputs are exactly representable in FP16 at these
+# magnitudes) and rounds its output to FP16; a BF16 output carries 8 significand bits, i.e. half an ulp is
+# 3.9e-3 for |o| in [1, 2) and 2e-3 below 1, and P is rounded to BF16 (relative 2^-9) before P.V.
+# max-abs <= 1.6e-2 (two BF16 ulps at |o| < 2), mean-abs <= 1.5e-3.
+BF16_MAX_ABS, BF16_MEAN_ABS = 1.6e-2, 1.5e-3
+
+
+@pytest.mark.parametrize("B,H,N,D,causal", [(1, 4, 1024, 128, 1), (2, 3, 777, 128, 0), (2, 2, 2048, 64, 1),
+                                            (1, 2, 4500, 128, 1), (1, 1, 129, 64, 0)])
+def test_bf16_operands(fa, B, H, N, D, causal):
+    rng = np.random.default_rng(5 + N)
+    x = [rng.standard_normal((B, H, N, D), dtype=np.float32) for _ in range(3)]
+    x[2] *= 0.5
+    tb = [torch.from_numpy(a).bfloat16() for a in x]
+    q16, k16, v16 = (t.float().numpy().astype(np.float16) for t in tb)
+    for t, h in zip(tb, (q16, k16, v16)):      # the FP16 copies hold the same values (up to FP16 subnormals)
+        assert np.abs(t.float().numpy() - h.astype(np.float32)).max() < 1e-7
+    ref = _oracle.attention(q16, k16, v16, causal)
+    before = fa.launch_count()
+    out = fa.flash_attn_fwd(*(t.cuda() for t in tb), causal=bool(causal))
+    torch.cuda.synchronize()
+    assert fa.launch_count() == before + 1 and out.dtype == torch.bfloat16
+    assert not fa.watchdog_status()["aborted"]
+    got = out.float().cpu().numpy()
+    assert not np.isnan(got).any()
+    d = np.abs(got - ref.astype(np.float32))
+    assert d.max() <= BF16_MAX_ABS and d.mean() <= BF16_MEAN_ABS, (d.max(), d.mean())
+    # and it is a different computation from the FP16 path: P and O really are BF16
+    out16 = fa.flash_attn_fwd(*(torch.from_numpy(h).cuda() for h in (q16, k16, v16)), causal=bool(causal))
+    assert (out16.float().cpu().numpy() != got).any()

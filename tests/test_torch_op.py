@@ -14,6 +14,12 @@ def test_op_is_registered_and_meta_kernel_describes_the_output():
     q = torch.empty((2, 3, 100, 128), dtype=torch.float16, device="meta")
     o = torch.ops.flashattn_b200.fwd(q, q, q, True)
     assert o.shape == q.shape and o.dtype == torch.float16 and o.device.type == "meta"
+    qb = q.to(torch.bfloat16)
+    assert torch.ops.flashattn_b200.fwd(qb, qb, qb, False).dtype == torch.bfloat16
+    with pytest.raises((TypeError, RuntimeError)):
+        torch.ops.flashattn_b200.fwd(qb, q, q, True)          # mixed operand types
+    with pytest.raises((TypeError, RuntimeError)):
+        torch.ops.flashattn_b200.fwd(q.float(), q.float(), q.float(), True)
     with pytest.raises((ValueError, RuntimeError)):
         torch.ops.flashattn_b200.fwd(torch.empty((2, 3, 100, 96), dtype=torch.float16, device="meta"), q, q, True)
 
