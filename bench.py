@@ -125,7 +125,7 @@ class ClockSampler:
 def ncu_traffic(workload_name):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
     capture of this workload's kernel (profiles/), or None when no capture of it is committed."""
-    captures = {"cfg2_n8192_causal": "r01_v4b_causal_n8192_summary.txt"}
+    captures = {"cfg2_n8192_causal": "r01_v4c_causal_n8192_summary.txt"}
     f = captures.get(workload_name)
     if not f:
         return None
