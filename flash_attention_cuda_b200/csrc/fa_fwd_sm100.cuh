@@ -101,7 +101,7 @@ struct Cfg {
     static constexpr int kSmemQ = 4 * kTileBytes;
     static constexpr int kSmemKV = kStages * kTileBytes;
     static constexpr int kBarOffset = kSmemQ + kSmemKV;
-    static constexpr int kNumBars = 4 + 2 * kStages + 12 + 4 + 4;
+    static constexpr int kNumBars = 4 + 2 * kStages + 14 + 4 + 4;
     static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 32 + 1024;  // +32: tmem slot, scheduler slots; +1024: manual alignment slack
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
     static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
@@ -245,10 +245,171 @@ __device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64
     }
 }
 
+#ifdef FA_SUM_GUARD
+// ---- softmax of one 128x128 S tile without a row max (one thread owns one row) ----
+// The reference kernel takes the row max of every tile and rescales O every tile (FA.cu:256-270); the lazy form
+// above still pays 61 FMNMX3 + a vote per tile on the critical path S -> P.  But the max is only needed to keep
+// exp2(s - m_ref) inside the FP16 range, and the row SUM of the exponentials -- which the algorithm needs anyway
+// (FA.cu:273-279) -- bounds every one of them: sum <= 2^13 means every p <= 2^13 < 65504, with FP16's relative
+// precision intact.  So: exponentials against the current m_ref, check the running tile sum before a piece of P is
+// stored, and only when it trips (first tile of a row, or scores that outgrew m_ref by ~2^13) take the slow path:
+// reload S from TMEM (P has not overwritten those columns yet), take the true max, rescale O and l, redo the piece.
+// A trip in the second piece finds the first one already published: O is then rescaled between the two pieces' PV
+// MMAs, behind the o_half commit the MMA warp issues after the first piece's k-steps.
+constexpr float kTripSum = 8192.0f;
+
+template <int kFrom, int kTo>
+__device__ __forceinline__ float row_max(const uint32_t* s) {
+    float mx0 = fmaxf(__uint_as_float(s[kFrom + 0]), __uint_as_float(s[kFrom + 1]));
+    float mx1 = fmaxf(__uint_as_float(s[kFrom + 2]), __uint_as_float(s[kFrom + 3]));
+    float mx2 = fmaxf(__uint_as_float(s[kFrom + 4]), __uint_as_float(s[kFrom + 5]));
+    float mx3 = fmaxf(__uint_as_float(s[kFrom + 6]), __uint_as_float(s[kFrom + 7]));
+#pragma unroll
+    for (int i = kFrom + 8; i < kTo; i += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+    }
+    return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+}
+
+template <int D>
+__device__ __forceinline__ void rescale_o(uint32_t tO, float alpha) {
+    const uint64_t alpha2 = pack_f32x2(alpha, alpha);
+#pragma unroll 1
+    for (int c = 0; c < D; c += 32) {
+        uint32_t o[32];
+        tmem_ld_x32(tO + c, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float lo, hi;
+            unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), lo, hi);
+            o[i] = __float_as_uint(lo);
+            o[i + 1] = __float_as_uint(hi);
+        }
+        tmem_st_x32(tO + c, o);
+    }
+}
+
+__device__ __forceinline__ float hsum_f32x2(uint64_t a, uint64_t b) {
+    float x, y;
+    unpack_f32x2(add_f32x2(a, b), x, y);
+    return x + y;
+}
+
+template <int D, bool kMask, int kPoly, bool kBF16>
+__device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
+                                             uint32_t bar_o_full, uint32_t bar_o_half, int lim_local, bool have_o,
+                                             uint32_t pv_count, float& m_ref, float& l_run) {
+    static_assert(kPParts == 2, "the sum-guarded softmax delivers P in two pieces");
+    uint32_t s[kBlockN];
+    tmem_ld_x32(tS + 0, s + 0);
+    tmem_ld_x32(tS + 32, s + 32);
+    tmem_ld_x32(tS + 64, s + 64);
+    tmem_ld_x32(tS + 96, s + 96);
+    tmem_wait_ld();
+
+    if (kMask) {
+#pragma unroll
+        for (int i = 0; i < kBlockN; i++)
+            if (i >= lim_local) s[i] = 0xff800000u;  // -inf
+    }
+    const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+    auto publish = [&](int part) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(bar_p_full + 8 * part);   // one arrival per warp (barrier count 4)
+    };
+    auto shift2 = [&]() {
+        const float m_used = (m_ref == -INFINITY) ? 0.0f : m_ref;
+        const float neg = -m_used * p.scale_log2;
+        return pack_f32x2(neg, neg);
+    };
+
+    // ---- piece 0: keys 0-63 -> TMEM columns [0,32)
+    uint64_t sum_a, sum_b;
+    uint32_t pk[32];
+    float sum0;
+#pragma unroll 1
+    for (int pass = 0;; ++pass) {
+        if (pass == 1 || have_o) {      // first tile of an item: no reference yet, nothing to speculate on
+            sum_a = 0ull;
+            sum_b = 0ull;
+            exp_half<kPoly, kBF16>(s, pk, scale2, shift2(), sum_a, sum_b);
+            sum0 = hsum_f32x2(sum_a, sum_b);
+            if (pass == 1) break;
+            const bool bad = !(sum0 <= kTripSum) || m_ref == -INFINITY;   // NaN trips as well
+            if (!__any_sync(0xffffffffu, bad)) break;
+        }
+        // slow path (warp-uniform): true max of the whole tile, O and l follow the new reference
+        tmem_ld_x32(tS + 0, s + 0);
+        tmem_ld_x32(tS + 32, s + 32);
+        tmem_wait_ld();
+        if (kMask) {
+#pragma unroll
+            for (int i = 0; i < 64; i++)
+                if (i >= lim_local) s[i] = 0xff800000u;
+        }
+        const float m_new = fmaxf(m_ref, row_max<0, kBlockN>(s));
+        if (have_o) {
+            const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
+            // O_t holds PV(0..j-1); the last of them must have retired before we touch it
+            mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 40);
+            tc_fence_after();
+            rescale_o<D>(tO, alpha);
+            l_run *= alpha;
+        }
+        m_ref = m_new;
+    }
+    tmem_st_x32(tS, pk);
+
+    // ---- piece 1: keys 64-127 -> columns [32,64); piece 0 is published a quarter tile in
+    uint32_t pk2[32];
+    float tile_sum;
+    {
+        const uint64_t neg2 = shift2();
+        sum_a = 0ull;
+        sum_b = 0ull;
+        exp_half<kPoly, kBF16, 32>(s + 64, pk2, scale2, neg2, sum_a, sum_b);
+        publish(0);
+        exp_half<kPoly, kBF16, 32>(s + 96, pk2 + 16, scale2, neg2, sum_a, sum_b);
+        tile_sum = sum0 + hsum_f32x2(sum_a, sum_b);
+    }
+    if (__any_sync(0xffffffffu, !(tile_sum <= kTripSum))) {
+        // slow path: piece 0 is already with the MMA warp under the old reference
+        tmem_ld_x32(tS + 64, s + 64);       // S columns [64,128) are untouched by P
+        tmem_ld_x32(tS + 96, s + 96);
+        tmem_wait_ld();
+        if (kMask) {
+#pragma unroll
+            for (int i = 64; i < kBlockN; i++)
+                if (i >= lim_local) s[i] = 0xff800000u;
+        }
+        const float m_new = fmaxf(m_ref, row_max<64, kBlockN>(s));
+        const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
+        mbar_wait(bar_o_half, pv_count & 1u, 41);      // PV of piece 0 of THIS tile (and everything before it) retired
+        tc_fence_after();
+        rescale_o<D>(tO, alpha);
+        l_run *= alpha;
+        sum0 *= alpha;
+        m_ref = m_new;
+        sum_a = 0ull;
+        sum_b = 0ull;
+        exp_half<kPoly, kBF16>(s + 64, pk2, scale2, shift2(), sum_a, sum_b);
+        tile_sum = sum0 + hsum_f32x2(sum_a, sum_b);
+    }
+    tmem_st_x32(tS + 32, pk2);
+    publish(1);
+    l_run += tile_sum;
+}
+#else
 // ---- softmax of one 128x128 S tile; one thread owns one row ----
 template <int D, bool kMask, int kPoly, bool kBF16>
 __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
-                                             uint32_t bar_o_full, int lim_local, bool have_o,
+                                             uint32_t bar_o_full, uint32_t /*bar_o_half*/, int lim_local, bool have_o,
                                              uint32_t pv_count, float& m_ref, float& l_run) {
     uint32_t s[kBlockN];
     tmem_ld_x32(tS + 0, s + 0);
@@ -344,6 +505,7 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
     l_run += a0 + a1;
 }
+#endif  // FA_SUM_GUARD
 
 template <int D, int kPoly, bool kBF16 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -363,7 +525,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t bar_s_full = bar_kv_empty + 8 * C::kStages;    // [tile]
     const uint32_t bar_p_full = bar_s_full + 16;                  // [tile][piece]  index 4*t + piece
     const uint32_t bar_o_full = bar_p_full + 64;                  // [tile]
-    const uint32_t bar_o_staged = bar_o_full + 16;                // [Q slot][tile] softmax warps -> store warp
+    const uint32_t bar_o_half = bar_o_full + 16;                  // [tile] PV of the first piece of P retired (sum-guard slow path)
+    const uint32_t bar_o_staged = bar_o_half + 16;                // [Q slot][tile] softmax warps -> store warp
     const uint32_t bar_sched_full = bar_o_staged + 32;            // [2] work-index slots, producer -> everyone
     const uint32_t bar_sched_empty = bar_sched_full + 16;         // [2]
     const uint32_t tmem_slot = bar_sched_empty + 16;
@@ -395,6 +558,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             for (int part = 0; part < 4; part++)
                 mbar_init(bar_p_full + 32 * t + 8 * part, 4);   // one arrival per softmax warp of the tile, per piece of P
             mbar_init(bar_o_full + 8 * t, 1);
+            mbar_init(bar_o_half + 8 * t, 1);
             mbar_init(bar_o_staged + 8 * t, 4);       // one arrival per softmax warp of the tile,
             mbar_init(bar_o_staged + 8 * (2 + t), 4); // per Q slot
         }
@@ -520,7 +684,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         // O_t (+)= P_t V_j : 8 k-steps of 16 kv rows (P k-step = 8 TMEM columns, V k-step = 16 rows * 128 B),
         // issued piece by piece as the pieces of P arrive
         auto issue_pv = [&](uint32_t tO, uint32_t tP, uint32_t v_smem, bool accumulate, uint32_t bar_p,
-                            uint32_t parity, uint32_t bar_o, int tag) {
+                            uint32_t parity, uint32_t bar_o, uint32_t bar_oh, int tag) {
             const uint64_t vdesc = umma_smem_desc(v_smem, C::kPanelBytes, 1024);
 #pragma unroll
             for (int part = 0; part < kPParts; part++) {
@@ -531,6 +695,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     for (int ks = p_part_ks(part); ks < p_part_ks(part + 1); ks++)
                         umma_ts(tO, tP + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV | (kBF16 ? C::kBf16Operands : 0u),
                                 (accumulate || ks > 0) ? 1u : 0u);
+#ifdef FA_SUM_GUARD
+                    if (part == 0) umma_commit(bar_oh);
+#endif
                     if (part == kPParts - 1) umma_commit(bar_o);
                 }
                 __syncwarp();
@@ -580,7 +747,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
                 // ---- tile 0: PV0(j), QK0(j+1)
                 if (j < n0) {
-                    issue_pv(tO0, tS0, v_smem, j > 0, bar_p_full, p_phase0, bar_o_full, 13);
+                    issue_pv(tO0, tS0, v_smem, j > 0, bar_p_full, p_phase0, bar_o_full, bar_o_half, 13);
                     p_phase0 ^= 1u;
                 }
                 if (has_next) {
@@ -590,7 +757,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 if (j + 1 < n0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
                 // ---- tile 1: PV1(j), QK1(j+1)
                 if (j < n1) {
-                    issue_pv(tO1, tS1, v_smem, j > 0, bar_p_full + 32, p_phase1, bar_o_full + 8, 14);
+                    issue_pv(tO1, tS1, v_smem, j > 0, bar_p_full + 32, p_phase1, bar_o_full + 8, bar_o_half + 8, 14);
                     p_phase1 ^= 1u;
                 }
                 commit(bar_kv_empty + 8 * rv.idx);
@@ -653,6 +820,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const uint32_t my_s_full = bar_s_full + 8 * t;
         const uint32_t my_p_full = bar_p_full + 32 * t;        // + 8 * piece
         const uint32_t my_o_full = bar_o_full + 8 * t;
+        const uint32_t my_o_half = bar_o_half + 8 * t;
         uint32_t s_phase = 0;
         uint32_t pv_count = 0;   // P tiles handed to the MMA warp so far == o_full completions expected
 
@@ -684,9 +852,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 const int k0 = j * kBlockN;
                 const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
                 if (need_mask)
-                    softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, lim - k0, j > 0, pv_count, m_ref, l_run);
+                    softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, lim - k0, j > 0, pv_count, m_ref, l_run);
                 else
-                    softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, kBlockN, j > 0, pv_count, m_ref, l_run);
+                    softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, kBlockN, j > 0, pv_count, m_ref, l_run);
                 ++pv_count;
 #ifdef FA_TIMING
                 if (lane == 0 && (warp & 3) == 0 && j > 0 && (j & 7) == 0) {   // sampled: 1 tile in 8

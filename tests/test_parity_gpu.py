@@ -102,6 +102,24 @@ def test_increasing_scores_force_rescale_every_tile(fa):
         gate(gpu_attention(fa, q, k, v, causal), _oracle.attention(q, k, v, causal))
 
 
+@pytest.mark.parametrize("D,step_at,jump", [(128, 64, 12.0), (128, 0, 12.0), (64, 64, 20.0), (128, 96, 30.0)])
+def test_score_steps_at_half_tile_boundaries(fa, D, step_at, jump):
+    """Scaled scores are flat and then jump by `jump` nats every 128 keys, at key 128*t + step_at: with step_at = 64
+    the second half of every KV tile outgrows whatever reference the first half was exponentiated against (an O
+    rescale between the two halves' PV MMAs), with 0 the whole tile does, with 96 the jump sits inside a half."""
+    N = 1024
+    rng = np.random.default_rng(3)
+    level = jump * np.floor((np.arange(N) + (128 - step_at)) / 128.0)           # nats, per key
+    q = np.ones((1, 2, N, D), np.float32)
+    q[:, 1] *= 0.5                                                               # second head: half the contrast
+    k = np.broadcast_to((level / np.sqrt(D))[None, None, :, None], (1, 2, N, D)).astype(np.float32)
+    k = k + rng.standard_normal((1, 2, N, D), dtype=np.float32) * 0.02
+    v = rng.standard_normal((1, 2, N, D), dtype=np.float32) * 0.5
+    q, k, v = q.astype(np.float16), k.astype(np.float16), v.astype(np.float16)
+    for causal in (0, 1):
+        gate(gpu_attention(fa, q, k, v, causal), _oracle.attention(q, k, v, causal), f"D{D} step@{step_at} causal={causal}")
+
+
 def test_causal_row0_equals_v0(fa):
     q, k, v = _oracle.fill_ref_rand((1, 8, 300, 128), 42)
     out = gpu_attention(fa, q, k, v, 1)
