@@ -19,7 +19,8 @@ namespace {
 
 constexpr int kMaxDevices = 64;
 constexpr int kSchedSlots = 4096;
-constexpr int kHostChunks = 8;     // head chunks flash_attn_fwd_host pipelines over PCIe
+constexpr int kHostChunks = 32;    // most head chunks flash_attn_fwd_host can pipeline over PCIe (events are per chunk)
+constexpr int kHostChunksDefault = 8;   // FLASH_ATTN_B200_HOST_CHUNKS overrides (A/B runs)
 constexpr int kGroupMB = 32;       // K+V bytes of one scheduling group of heads (make_params)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -392,7 +393,12 @@ int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho
     // chunk c+1 is on its way in and chunk c-1 on its way out (PCIe is full duplex; three streams,
     // one event pair per chunk).  The wire time of Q, K, V dominates; kernels and O hide under it.
     const int BH = B * H;
-    const int chunks = BH < kHostChunks ? BH : kHostChunks;
+    static const int want_chunks = [] {
+        const char* e = getenv("FLASH_ATTN_B200_HOST_CHUNKS");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= kHostChunks ? v : kHostChunksDefault;
+    }();
+    const int chunks = BH < want_chunks ? BH : want_chunks;
     const size_t head_bytes = (size_t)N * D * sizeof(__half);
     int h0 = 0;
     for (int c = 0; c < chunks; c++) {
