@@ -1,3 +1,4 @@
+# A/B: P delivered in 2 vs 3 pieces, setmaxnreg 216/72 (variant libs built into build/ with -DFA_P_PARTS / -DFA_REGS_*), then the GPU parity suite on both
 set -x
 mkdir -p gpurun_out
 python tests/harness/ab_quick.py flash_attention_cuda_b200/libflashattn_b200.so build/lib_parts3.so build/lib_r216_72_parts2.so build/lib_r216_72_parts3.so > gpurun_out/ab_parts.log 2>&1

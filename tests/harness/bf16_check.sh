@@ -1,3 +1,4 @@
+# BF16 operand path: parity tests, then FP16 vs BF16 throughput on the same box
 set -x
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "bf16" > gpurun_out/bf16_pytest.log 2>&1; echo pytest rc=$?

@@ -1,3 +1,4 @@
+# 4-GPU scaling points: cfg5 with peer pulls, default workload (weak)
 set -x
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29517"
