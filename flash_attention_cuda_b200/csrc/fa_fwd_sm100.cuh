@@ -123,6 +123,7 @@ struct Params {
     int group_heads;    // heads per scheduling group (their K/V working set is sized to stay in L2)
     int partial_mode;
     int accumulate;
+    int zero;           // always 0: trip count of the empty loops that fence ptxas' instruction scheduler (FA_SCHED_FENCE)
     int* sched;         // {next work index, finished CTAs}: dynamic tile scheduler state, self-resetting
     float scale;        // 1/sqrt(D)
     float scale_log2;   // scale * log2(e)
@@ -167,6 +168,24 @@ __host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
 #ifdef FA_TIMING
 __device__ unsigned long long g_timing[32];
 #endif
+
+// ptxas schedules a basic block as a whole and gives the F2FP + tcgen05.st of the first piece of P the lowest priority
+// (nothing in the block depends on them), so without a fence the first piece is stored after ~85 % of ALL the tile's
+// exponentials and the "PV of piece 0 under the exponentials of piece 1" overlap mostly disappears.  Loops and
+// volatile asm do not stop it (the exponentials are speculatable and get hoisted across them); a data dependency
+// does: the second piece's shift operand is OR-ed with (%clock & p.zero) -- p.zero is a kernel parameter that is
+// always 0 -- read behind the first piece's store.
+__device__ __forceinline__ uint64_t sched_fence(uint64_t v, int zero) {
+#ifndef FA_SCHED_FENCE
+    (void)zero;
+    return v;
+#else
+    uint32_t c;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(c)::"memory");
+    c &= (uint32_t)zero;
+    return v | ((uint64_t)c << 32) | (uint64_t)c;
+#endif
+}
 
 struct Ring {
     uint32_t idx, phase;
@@ -487,10 +506,11 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     uint32_t pk2[32];
     exp_half<kPoly, kBF16>(s, pk, scale2, neg2, sum_a, sum_b);
     tmem_st_x32(tS, pk);
-    exp_half<kPoly, kBF16, 32>(s + 64, pk2, scale2, neg2, sum_a, sum_b);
+    const uint64_t neg2b = sched_fence(neg2, p.zero);      // piece 1 may not start before piece 0 is on its way
+    exp_half<kPoly, kBF16, 32>(s + 64, pk2, scale2, neg2b, sum_a, sum_b);
     publish(0);
     if (kPParts == 2) {
-        exp_half<kPoly, kBF16, 32>(s + 96, pk2 + 16, scale2, neg2, sum_a, sum_b);
+        exp_half<kPoly, kBF16, 32>(s + 96, pk2 + 16, scale2, neg2b, sum_a, sum_b);
         tmem_st_x32(tS + 32, pk2);
         publish(1);
     } else {
@@ -870,6 +890,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             if (n_t > 0) {
                 mbar_wait(my_o_full, (pv_count - 1u) & 1u, 30 + t);
                 tc_fence_after();
+            } else {
+                // No key visible to this tile (a K/V block entirely in its future): nothing above waited for the
+                // item's Q pair to land, and the epilogue stages its rows in that very buffer.  Without this wait the
+                // tail of the TMA load overwrites the staged rows of the tile's last warp (seen as a few wrong rows in
+                // the in-place accumulate sequence, tests/harness/accumulate_stress.py).
+                mbar_wait(bar_q_full + 8 * (it & 1u), (it >> 1) & 1u, 32 + t);
             }
             const bool row_ok = row < p.Nq;
             const size_t grow = (size_t)wi.bh * p.Nq + row;
@@ -907,8 +933,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 float l_out = l_run;
                 float w_new = 1.f, w_old = 0.f;
                 if (p.accumulate && row_ok) {
-                    const float m_old = p.ml[grow * 2 + 0];
-                    const float l_old = p.ml[grow * 2 + 1];
+                    // written by an earlier launch, possibly from another SM: read at L2 like the O partials below
+                    const float2 ml_old = __ldcg(reinterpret_cast<const float2*>(p.ml + grow * 2));
+                    const float m_old = ml_old.x;
+                    const float l_old = ml_old.y;
                     const float m_max = fmaxf(m_old, m_out);
                     const float kLog2e = 1.4426950408889634f;
                     w_old = (m_old <= -FLT_MAX) ? 0.f : ex2_approx((m_old - m_max) * kLog2e);

@@ -424,3 +424,28 @@ def test_bf16_operands(fa, B, H, N, D, causal):
     # and it is a different computation from the FP16 path: P and O really are BF16
     out16 = fa.flash_attn_fwd(*(torch.from_numpy(h).cuda() for h in (q16, k16, v16)), causal=bool(causal))
     assert (out16.float().cpu().numpy() != got).any()
+
+
+def test_accumulate_sequence_repeated_matches_monolithic(fa):
+    """K/V blocks entirely in the future of a Q tile give that tile nothing to do; its epilogue still stages rows in the
+    item's Q buffer and must wait for the Q load to have landed (a race seen as single wrong rows in ~3 % of runs,
+    profiles/r01_accumulate_race.txt).  Repeats the in-place accumulate sequence and compares with one launch."""
+    B, H, N, D, P = 1, 8, 2048, 128, 4
+    blk = N // P
+    for it in range(12):
+        g = torch.Generator(device="cuda").manual_seed(500 + it)
+        q, k = (torch.randn((B, H, N, D), device="cuda", generator=g).half() for _ in range(2))
+        v = (torch.randn((B, H, N, D), device="cuda", generator=g) * 0.5).half()
+        full = fa.flash_attn_fwd(q, k, v, causal=True)
+        o_part = torch.full((B * H * N, D), float("nan"), dtype=torch.float32, device="cuda")
+        ml = torch.full((B * H * N, 2), float("nan"), dtype=torch.float32, device="cuda")
+        for s in range(P):
+            ks = k[:, :, s * blk:(s + 1) * blk].contiguous()
+            vs = v[:, :, s * blk:(s + 1) * blk].contiguous()
+            fa.flash_attn_fwd_partial(q, ks, vs, o_part, ml, True, 0, s * blk, accumulate=(s > 0))
+        out = torch.empty_like(q)
+        fa.flash_attn_finalize(o_part, ml, out)
+        torch.cuda.synchronize()
+        assert not fa.watchdog_status()["aborted"]
+        d = (out.float() - full.float()).abs().max().item()
+        assert d <= 1e-3, f"iteration {it}: accumulate sequence differs from the monolithic kernel by {d:.3e}"
