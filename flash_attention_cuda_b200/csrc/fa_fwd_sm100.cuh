@@ -35,6 +35,15 @@
 // Why not 64-wide KV sub-tiles with S double-buffered (tried, profiles/r01_v3_subtile_*): QK^T with
 // N=64 in SS mode re-reads the Q slice from shared memory for half the math (192 B/clk > the 128 B/clk
 // smem port).  N=128 sits exactly at the port limit, so the S->P->PV->QK chain is shortened instead.
+//
+// Build-time switches (all off in the product build; each one is an experiment recorded under profiles/):
+//   -DFA_TIMING        in-kernel clock64 probes (tests/harness/timing.py)
+//   -DFA_SKELETON / -DFA_NO_EXP   exponentials replaced by the identity (what the tensor side alone can do)
+//   -DFA_SUM_GUARD     softmax without a row max, guarded by the row sum (r01_v4c_sumguard_experiment.txt)
+//   -DFA_SCHED_FENCE   data-dependency fence that makes ptxas store the first piece of P before the second
+//                      piece's exponentials (r01_accumulate_race.txt)
+//   -DFA_P_PARTS=3     P in three pieces;  -DFA_REGS_SOFTMAX / -DFA_REGS_OTHER  setmaxnreg budgets
+//                      (r01_v4b_defer_group_ab.log)
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
