@@ -1,0 +1,113 @@
+// Microbenchmark of fa::softmax_tile (the S -> P step of the kernel) in isolation: no MMA, no TMA.
+// Eight warps as in the kernel (warps 0-3 = Q tile 0, 4-7 = Q tile 1, one of each per SM sub-partition); every
+// iteration refills the tile's S columns in TMEM, runs the real softmax_tile on them and then idles `gap` cycles
+// (the kernel's wait for PV + QK^T of its own tile, ~935 cycles).  Reports cycles per softmax_tile call for
+//   solo  : only the warps of tile 0 run
+//   dual  : both tiles, tile 1 started half a period later (the kernel's steady state)
+//   lock  : both tiles in lock-step (worst case for the shared MUFU)
+// Build variants with the kernel's own switches (-DFA_SUM_GUARD, -DFA_SCHED_FENCE, ...):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o softmax_bench tests/harness/micro/softmax_bench.cu
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../../flash_attention_cuda_b200/csrc/fa_fwd_sm100.cuh"
+
+using namespace fa;
+
+template <int kPoly>
+__global__ void __launch_bounds__(256, 1)
+bench(Params p, unsigned long long* out, int iters, int active_mask, int offset1, int gap) {
+    __shared__ alignas(8) unsigned long long bars[16];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; i++) mbar_init(smem_u32(&bars[i]), 4);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(smem_u32(&tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const int t = warp >> 2;
+    unsigned long long total = 0, calls = 0;
+    if ((active_mask >> t) & 1) {
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem_base + lane_base + (t ? 128 : 0);
+        const uint32_t tO = tmem_base + lane_base + 256 + 128 * t;
+        const uint32_t bar_p = smem_u32(&bars[4 * t]);          // p_full pieces: arrivals only, nobody waits
+        const uint32_t bar_o = smem_u32(&bars[8 + t]), bar_oh = smem_u32(&bars[10 + t]);
+        float m_ref = -INFINITY, l_run = 0.f;
+        uint32_t pv = 0;
+        if (t == 1) {
+            const long long s0 = clock64();
+            while (clock64() - s0 < offset1) { }
+        }
+        for (int it = 0; it < iters; it++) {
+            // refill S: scores in [-2, 2), the row maximum (2.0) always at key 0 -> no rescale after the first tile
+            for (int c = 0; c < 4; c++) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    uint32_t h = (uint32_t)(it * 131 + c * 32 + i) * 2654435761u + (uint32_t)threadIdx.x * 40503u;
+                    v[i] = __float_as_uint(((h >> 9) & 0x7fff) * (4.0f / 32768.0f) - 2.0f);
+                }
+                if (c == 0) v[0] = __float_as_uint(2.0f);
+                tmem_st_x32(tS + 32 * c, v);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            tc_fence_after();
+            const long long t0 = clock64();
+            softmax_tile<128, false, kPoly, false>(p, tS, tO, bar_p, bar_o, bar_oh, 128, it > 0, pv, m_ref, l_run);
+            const long long t1 = clock64();
+            ++pv;
+            if (it >= 4) { total += (unsigned long long)(t1 - t0); ++calls; }
+            while (clock64() - t1 < gap) { }
+        }
+        if (lane == 0) { out[warp * 2] = total; out[warp * 2 + 1] = calls; }
+        if (l_run == 123.456f) out[63] = 1;     // keep the result alive
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int kPoly>
+void run(const char* name, int mask, int offset1, int gap) {
+    Params p;
+    memset(&p, 0, sizeof p);
+    p.scale = 1.0f / sqrtf(128.f);
+    p.scale_log2 = p.scale * 1.4426950408889634f;
+    unsigned long long* d;
+    cudaMalloc(&d, 64 * 8);
+    cudaMemset(d, 0, 64 * 8);
+    bench<kPoly><<<1, 256>>>(p, d, 400, mask, offset1, gap);
+    unsigned long long h[64];
+    cudaError_t e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    printf("  poly %d  %-5s gap %4d:", kPoly, name, gap);
+    for (int w = 0; w < 8; w += 4)
+        if (h[w * 2 + 1]) printf("  tile %d %6.0f cyc/softmax_tile", w / 4, (double)h[w * 2] / h[w * 2 + 1]);
+    printf("  %s\n", e == cudaSuccess ? "" : cudaGetErrorString(e));
+    cudaFree(d);
+}
+
+int main(int argc, char** argv) {
+    const int gap = argc > 1 ? atoi(argv[1]) : 935;
+    printf("%s\n", argc > 2 ? argv[2] : "softmax_tile microbenchmark");
+    run<1>("solo", 1, 0, gap);
+    run<1>("dual", 3, 1300, gap);
+    run<1>("lock", 3, 0, gap);
+    run<0>("solo", 1, 0, gap);
+    run<0>("dual", 3, 1300, gap);
+    run<1>("solo", 1, 0, 0);
+    run<1>("lock", 3, 0, 0);
+    return 0;
+}
