@@ -513,6 +513,36 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
         if (lane_id() == 0) mbar_arrive(bar_p_full + 8 * part);   // one arrival per warp (barrier count 4)
     };
     uint32_t pk2[32];
+#ifdef FA_STREAM_S
+    // Variant: the second half of S is not kept in registers across the first half's exponentials but read again
+    // from TMEM (P only ever covers columns [0,64) of S_t, so columns [64,128) stay intact for the whole tile).
+    // 64 fewer live registers while the first piece is computed: room for ptxas to keep MUFU results in flight
+    // instead of consuming a third of them within 4-7 instructions (profiles/r01_softmax_schedule.txt).
+    {
+        static_assert(kPParts == 2, "");
+        uint32_t hi[64];
+        exp_half<kPoly, kBF16, 48>(s, pk, scale2, neg2, sum_a, sum_b);
+        tmem_ld_x32(tS + 64, hi);                 // lands under the last quarter of the first piece
+        tmem_ld_x32(tS + 96, hi + 32);
+        exp_half<kPoly, kBF16, 16>(s + 48, pk + 24, scale2, neg2, sum_a, sum_b);
+        tmem_st_x32(tS, pk);
+        tmem_wait_ld();
+        if (kMask) {
+#pragma unroll
+            for (int i = 0; i < 64; i++)
+                if (64 + i >= lim_local) hi[i] = 0xff800000u;
+        }
+        exp_half<kPoly, kBF16, 32>(hi, pk2, scale2, neg2, sum_a, sum_b);
+        publish(0);
+        exp_half<kPoly, kBF16, 32>(hi + 32, pk2 + 16, scale2, neg2, sum_a, sum_b);
+        tmem_st_x32(tS + 32, pk2);
+        publish(1);
+        float a0, a1;
+        unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
+        l_run += a0 + a1;
+        return;
+    }
+#endif
     exp_half<kPoly, kBF16>(s, pk, scale2, neg2, sum_a, sum_b);
     tmem_st_x32(tS, pk);
     const uint64_t neg2b = sched_fence(neg2, p.zero);      // piece 1 may not start before piece 0 is on its way
