@@ -160,7 +160,14 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     if (shift > 0x3fffffffLL) shift = 0x3fffffffLL;
     if (shift < -0x3fffffffLL) shift = -0x3fffffffLL;
     p.shift = (int)shift;
-    p.nqp = (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
+    // experimental: one Q tile per work item (shorter dependency chains for grids that cannot fill the machine);
+    // off unless FLASH_ATTN_B200_ITEM_TILES=1 -- not yet measured on a GPU
+    static const int single = [] {
+        const char* e = getenv("FLASH_ATTN_B200_ITEM_TILES");
+        return e && atoi(e) == 1 ? 1 : 0;
+    }();
+    p.single = single;
+    p.nqp = single ? (Nq + fa::kBlockM - 1) / fa::kBlockM : (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
     const long long tw = (long long)BH * p.nqp;
     p.total_work = (int)tw;
     // heads per scheduling group: K+V of the group <= kGroupMB (B200's 126 MB L2 is two 63 MB halves, and a line
@@ -616,5 +623,6 @@ extern "C" int flash_attn_debug_work_item(int w, int B, int H, int Nq, int Nkv, 
 // kernel the CTAs per unit (1 or 2), each holding one tile
 extern "C" int flash_attn_debug_tiles_per_item(int D) {
     if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
-    return use_pair_kernel() ? pair_cta_group_for(D) : 2;
+    if (use_pair_kernel()) return pair_cta_group_for(D);
+    return make_params(1, 1, 1, D, 0, 0).single ? 1 : 2;
 }

@@ -127,7 +127,8 @@ struct Params {
     int Nq, Nkv, BH;
     int causal;
     int shift;          // q_offset - kv_offset: key c visible to query r iff c <= r + shift
-    int nqp;            // Q tile pairs per head = ceil(Nq / 256)
+    int nqp;            // work items per head: Q tile pairs, ceil(Nq / 256) (single: Q tiles, ceil(Nq / 128))
+    int single;         // 1: a work item is ONE Q tile (experimental, FLASH_ATTN_B200_ITEM_TILES=1; tile 1 of every item absent)
     int total_work;     // BH * nqp
     int group_heads;    // heads per scheduling group (their K/V working set is sized to stay in L2)
     int partial_mode;
@@ -142,6 +143,7 @@ struct Params {
 struct WorkItem {
     int bh, q0;      // head index, first local query row of the pair
     int n0, n1;      // KV tiles the two Q tiles need (0 = nothing visible / tile absent)
+    int tile1;       // the item has a second Q tile (rows q0+128..): false past the end of Q and in single-tile mode
 };
 __host__ __device__ inline int kv_trip_count(int q_start, int Nq, int Nkv, int causal, int shift) {
     if (q_start >= Nq) return 0;
@@ -168,9 +170,10 @@ __host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
     if (heads > p.group_heads) heads = p.group_heads;
     const int qp = p.nqp - 1 - r / heads;
     it.bh = g * p.group_heads + r % heads;
-    it.q0 = qp * 2 * kBlockM;
+    it.q0 = qp * (p.single ? 1 : 2) * kBlockM;
+    it.tile1 = !p.single && it.q0 + kBlockM < p.Nq;
     it.n0 = kv_trip_count(it.q0, p.Nq, p.Nkv, p.causal, p.shift);
-    it.n1 = kv_trip_count(it.q0 + kBlockM, p.Nq, p.Nkv, p.causal, p.shift);
+    it.n1 = it.tile1 ? kv_trip_count(it.q0 + kBlockM, p.Nq, p.Nkv, p.causal, p.shift) : 0;
     return it;
 }
 
@@ -688,7 +691,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
             const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
-            const bool have_q1 = wi.q0 + kBlockM < p.Nq;
+            const bool have_q1 = wi.tile1 != 0;
             // slot it&1 is free once the item two back has issued its last QK^T and stored its O tiles
             mbar_wait(bar_q_empty + 8 * slot, ((it >> 1) & 1u) ^ 1u, 1);
             if (elect_one()) {
@@ -848,7 +851,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
             for (int t = 0; t < 2; t++) {
                 const int q_start = wi.q0 + t * kBlockM;
-                if (q_start >= p.Nq) continue;                          // tile absent: nobody arrives, nothing to store
+                if (t == 1 && !wi.tile1) continue;                      // tile absent: nobody arrives, nothing to store
                 const uint32_t b = slot * 2 + t;
                 mbar_wait(bar_o_staged + 8 * b, (staged_parity >> b) & 1u, 60 + t);
                 staged_parity ^= 1u << b;
@@ -888,7 +891,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
             const int q_start = wi.q0 + t * kBlockM;
-            if (q_start >= p.Nq) continue;                     // this Q tile does not exist (the store warp knows)
+            if (t == 1 && !wi.tile1) continue;                 // this Q tile does not exist (the store warp knows)
             const int n_t = t ? wi.n1 : wi.n0;
             const int row = q_start + row_in_tile;             // local query row
             // keys [0, lim) are visible to this row

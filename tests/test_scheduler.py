@@ -97,3 +97,18 @@ def test_head_groups_are_equal_sized():
     bounds = [0, 7 * nqp, 14 * nqp, 20 * nqp]
     heads = [sorted({it["bh"] for it in its[a:b]}) for a, b in zip(bounds, bounds[1:])]
     assert heads == [list(range(0, 7)), list(range(7, 14)), list(range(14, 20))]
+
+
+def test_single_tile_work_items_cover_every_tile_too():
+    """FLASH_ATTN_B200_ITEM_TILES=1 (experimental: one Q tile per work item): the same decomposition tests in that mode."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("FLASH_ATTN_B200_ITEM_TILES") == "1":
+        pytest.skip("already in single-tile mode")
+    env = dict(os.environ, FLASH_ATTN_B200_ITEM_TILES="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                        "every_q_tile or masked_tiles or triangular or heavy_first"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert fa.tiles_per_item(128) == 2       # this process: default mode
