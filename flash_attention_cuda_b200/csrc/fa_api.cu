@@ -161,12 +161,18 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     if (shift < -0x3fffffffLL) shift = -0x3fffffffLL;
     p.shift = (int)shift;
     // experimental: one Q tile per work item (shorter dependency chains for grids that cannot fill the machine);
-    // off unless FLASH_ATTN_B200_ITEM_TILES=1 -- not yet measured on a GPU
+    // only in -DFA_SINGLE_TILE_MODE builds and with FLASH_ATTN_B200_ITEM_TILES=1 -- not yet measured on a GPU
+#ifdef FA_SINGLE_TILE_MODE
     static const int single = [] {
         const char* e = getenv("FLASH_ATTN_B200_ITEM_TILES");
         return e && atoi(e) == 1 ? 1 : 0;
     }();
+#else
+    const int single = 0;
+#endif
+#ifdef FA_SINGLE_TILE_MODE
     p.single = single;
+#endif
     p.nqp = single ? (Nq + fa::kBlockM - 1) / fa::kBlockM : (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
     const long long tw = (long long)BH * p.nqp;
     p.total_work = (int)tw;
@@ -624,5 +630,9 @@ extern "C" int flash_attn_debug_work_item(int w, int B, int H, int Nq, int Nkv, 
 extern "C" int flash_attn_debug_tiles_per_item(int D) {
     if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
     if (use_pair_kernel()) return pair_cta_group_for(D);
+#ifdef FA_SINGLE_TILE_MODE
     return make_params(1, 1, 1, D, 0, 0).single ? 1 : 2;
+#else
+    return 2;
+#endif
 }

@@ -42,6 +42,8 @@
 //   -DFA_SUM_GUARD     softmax without a row max, guarded by the row sum (r01_v4c_sumguard_experiment.txt)
 //   -DFA_SCHED_FENCE   data-dependency fence that makes ptxas store the first piece of P before the second
 //                      piece's exponentials (r01_accumulate_race.txt)
+//   -DFA_STREAM_S      second half of S re-read from TMEM instead of held in registers (r01_softmax_schedule.txt; not yet run)
+//   -DFA_SINGLE_TILE_MODE  one Q tile per work item, selected at run time by FLASH_ATTN_B200_ITEM_TILES=1 (not yet run)
 //   -DFA_P_PARTS=3     P in three pieces;  -DFA_REGS_SOFTMAX / -DFA_REGS_OTHER  setmaxnreg budgets
 //                      (r01_v4b_defer_group_ab.log)
 #pragma once
@@ -128,7 +130,9 @@ struct Params {
     int causal;
     int shift;          // q_offset - kv_offset: key c visible to query r iff c <= r + shift
     int nqp;            // work items per head: Q tile pairs, ceil(Nq / 256) (single: Q tiles, ceil(Nq / 128))
+#ifdef FA_SINGLE_TILE_MODE
     int single;         // 1: a work item is ONE Q tile (experimental, FLASH_ATTN_B200_ITEM_TILES=1; tile 1 of every item absent)
+#endif
     int total_work;     // BH * nqp
     int group_heads;    // heads per scheduling group (their K/V working set is sized to stay in L2)
     int partial_mode;
@@ -138,6 +142,14 @@ struct Params {
     float scale;        // 1/sqrt(D)
     float scale_log2;   // scale * log2(e)
 };
+
+// Single-tile work items are compiled in only with -DFA_SINGLE_TILE_MODE (and then selected at run time by
+// FLASH_ATTN_B200_ITEM_TILES=1): the product build keeps exactly the code that was measured.
+#ifdef FA_SINGLE_TILE_MODE
+#define FA_SINGLE(p) ((p).single)
+#else
+#define FA_SINGLE(p) 0
+#endif
 
 // ---- work decomposition (shared by host tests and every warp role) ----
 struct WorkItem {
@@ -170,8 +182,8 @@ __host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
     if (heads > p.group_heads) heads = p.group_heads;
     const int qp = p.nqp - 1 - r / heads;
     it.bh = g * p.group_heads + r % heads;
-    it.q0 = qp * (p.single ? 1 : 2) * kBlockM;
-    it.tile1 = !p.single && it.q0 + kBlockM < p.Nq;
+    it.q0 = qp * (FA_SINGLE(p) ? 1 : 2) * kBlockM;
+    it.tile1 = !FA_SINGLE(p) && it.q0 + kBlockM < p.Nq;
     it.n0 = kv_trip_count(it.q0, p.Nq, p.Nkv, p.causal, p.shift);
     it.n1 = it.tile1 ? kv_trip_count(it.q0 + kBlockM, p.Nq, p.Nkv, p.causal, p.shift) : 0;
     return it;

@@ -99,16 +99,25 @@ def test_head_groups_are_equal_sized():
     assert heads == [list(range(0, 7)), list(range(7, 14)), list(range(14, 20))]
 
 
-def test_single_tile_work_items_cover_every_tile_too():
-    """FLASH_ATTN_B200_ITEM_TILES=1 (experimental: one Q tile per work item): the same decomposition tests in that mode."""
+def test_single_tile_work_items_cover_every_tile_too(tmp_path):
+    """Experimental single-tile work items (a -DFA_SINGLE_TILE_MODE build + FLASH_ATTN_B200_ITEM_TILES=1): the same
+    decomposition tests in that mode.  The product build ignores the variable."""
     import os
+    import shutil
     import subprocess
     import sys
-    if os.environ.get("FLASH_ATTN_B200_ITEM_TILES") == "1":
-        pytest.skip("already in single-tile mode")
-    env = dict(os.environ, FLASH_ATTN_B200_ITEM_TILES="1")
+    assert fa.tiles_per_item(128) == 2
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = str(tmp_path / "libfa_single.so")
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-Xcompiler", "-fPIC",
+                    "-DFA_SINGLE_TILE_MODE", "-shared", os.path.join(repo, "flash_attention_cuda_b200", "csrc", "fa_api.cu"),
+                    "-o", lib], check=True, cwd=repo)
+    env = dict(os.environ, FLASH_ATTN_B200_ITEM_TILES="1", FLASH_ATTN_B200_LIB=lib)
+    code = ("import flash_attention_cuda_b200 as fa, sys; assert fa.tiles_per_item(128) == 1; "
+            "it = fa.work_item(0, 1, 32, 1024, 1024, 128, True); assert it['total'] == 256 and it['n1'] == 0, it")
+    subprocess.run([sys.executable, "-c", code], env=env, check=True, cwd=repo)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
-                        "every_q_tile or masked_tiles or triangular or heavy_first"], env=env, capture_output=True, text=True,
-                       timeout=600)
+                        "every_q_tile or masked_tiles or triangular"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-    assert fa.tiles_per_item(128) == 2       # this process: default mode
