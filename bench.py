@@ -43,8 +43,12 @@ WORKLOADS = {
     "cfg2_n16384_full": (1, 32, 16384, 128, 0),
     "cfg3_b16_n8192_causal": (16, 32, 8192, 128, 1),     # configs[2] (strong scaling: B*H sharded)
     "cfg4_d64_n2048_full": (32, 16, 2048, 64, 0),        # configs[3]
-    "cfg5_ring_n131072_causal": (1, 32, 131072, 128, 1),  # configs[4]: ring context parallel over the ranks
+    "cfg5_ring_n131072_causal": (1, 32, 131072, 128, 1),  # configs[4]: context parallel over the ranks
+    # the same shape with its 32 heads split across the ranks instead of its sequence: the no-communication upper bound
+    # SURVEY 8(e) asks to be reported next to the context-parallel number
+    "cfg5_heads_n131072_causal": (1, 32, 131072, 128, 1),
 }
+STRONG_BH_SHARD = ("cfg3_b16_n8192_causal", "cfg5_heads_n131072_causal")
 DEFAULT_WORKLOAD = "cfg2_n8192_causal"
 NOMINAL_FP16_TFLOPS = 2250.0
 
@@ -324,7 +328,7 @@ def main():
 
     if args.workload.startswith("cfg5_ring"):
         return bench_ring(args, workload, rank, world, local_rank, barrier)
-    if args.workload.startswith("cfg3") and world > 1:
+    if args.workload in STRONG_BH_SHARD and world > 1:
         # strong scaling: the B*H heads are split across ranks (no collective), total work fixed
         from flash_attention_cuda_b200.ring import bh_shard
         _, cnt = bh_shard(B * H, rank, world)
@@ -417,11 +421,11 @@ def main():
     out = {
         "metric": "fwd_tflops", "value": round(value, 2), "unit": "TFLOPS", "n_gpus": n_gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
-        "scaling": "strong" if (args.workload.startswith("cfg3") and world > 1) else "weak",
+        "scaling": "strong" if (args.workload in STRONG_BH_SHARD and world > 1) else "weak",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": args.workload, "B": B, "H": H, "N": N, "D": D, "causal": causal,
                    "per_gpu": "every rank runs the full workload on its own GPU (batch x heads shard, no collective)"
-                              if not (args.workload.startswith("cfg3") and world > 1) else
+                              if not (args.workload in STRONG_BH_SHARD and world > 1) else
                               "the workload's B*H heads are split across the ranks (no collective); B,H here are rank 0's share",
                    "l2": f"inputs {4 * nbytes / 2**20:.0f} MiB per step > 126 MB L2 (no flush needed)"
                          if 4 * nbytes > 126e6 else "inputs fit L2: hot-L2 timing, reference method (FA.cu:942-960)",
