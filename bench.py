@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the hot path: FlashAttention forward, FP16, on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cpu]
-                    [--workload NAME] [--sweep]
+                    [--workload NAME] [--sweep] [--sustain-s S] [--flush-l2] [--no-multi]
 
 One "step" = one forward pass over one synthetic batch of the named workload (default: the shape
 BASELINE.json's metric is quoted on -- B=1 H=32 D=128 seq=8192 causal, the README table's shape at
@@ -11,16 +11,28 @@ the north-star target length).  Prints ONE JSON line (rank 0):
   value     whole-job forward TFLOPS (FLOPs = 4*B*H*N^2*D, /2 causal -- the reference's convention,
             flash_attention.cu:938-939), inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       the same metric through the C-ABI call with HOST buffers (flash_attn_fwd_host: H2D of
-            Q,K,V from pinned memory + kernel + D2H of O inside the timed region)
-  roofline  tensor-bound: achieved TFLOPS of the kernel vs the measured cuBLAS bf16 peak
+            Q,K,V from pinned memory + kernel + D2H of O inside the timed region); `copy_only_ms` is the
+            same byte traffic with no kernel in between, all ranks at once: the host-side floor of the call
+  roofline  tensor-bound: achieved TFLOPS of the kernel vs the measured cuBLAS bf16 peak (burst figure:
+            the timed region is milliseconds long)
+  sustained a separate leg of >= --sustain-s seconds of back-to-back launches with its own clocks record,
+            against the measured SUSTAINED cuBLAS figure
   cpu_baseline  the CPU oracle (port of the reference's cpu_attention) on a bounded row sample
+
+Under torchrun (N > 1) the line additionally carries, measured in the same process group:
+  strong_cfg3   BASELINE config 3 (B16 H32 N8192 causal) with its 512 heads split over the ranks, no collective
+                (reference flash_attention.cu:120-122: heads are independent)
+  cp_cfg5       BASELINE config 5 (B1 H32 N131072 causal) context-parallel over the ranks, `pull` (copy-engine
+                reads of the peers' K/V) and `sendrecv` (NCCL ring), next to the no-communication bound
+                (the same shape with its heads split)
+  cp_parity     context-parallel output rows of every rank against the CPU oracle (gate 2e-3 / 2e-4;
+                the process exits non-zero when it fails)
 
 `--impl reference` runs the UNMODIFIED reference kernel (V9, flash_attention_v9_dispatch) rebuilt for
 sm_100a from /root/reference into oracle/_ref/libref_v9.so, on the same workload with the same timing
 code.  The reference's implementation of this path is a GPU kernel, so that is what the reference arm
 times; its CPU check function (cpu_attention) is reported beside it as `cpu_baseline`
-(`--impl reference-cpu` times only that).  Multi-GPU: every rank runs the workload on its own GPU
-(batch x heads shard, no collective on the data path) -> "scaling": "weak".
+(`--impl reference-cpu` times only that).
 """
 import argparse
 import ctypes
@@ -37,6 +49,9 @@ sys.path.insert(0, os.path.join(REPO, "tests"))
 WORKLOADS = {
     # name: (B, H, N, D, causal)
     "cfg1_n1024_causal": (1, 32, 1024, 128, 1),          # BASELINE.json configs[0]
+    "cfg2_n512_causal": (1, 32, 512, 128, 1),
+    "cfg2_n2048_causal": (1, 32, 2048, 128, 1),
+    "cfg2_n4096_causal": (1, 32, 4096, 128, 1),
     "cfg2_n8192_causal": (1, 32, 8192, 128, 1),          # configs[1], headline
     "cfg2_n8192_full": (1, 32, 8192, 128, 0),
     "cfg2_n16384_causal": (1, 32, 16384, 128, 1),
@@ -51,6 +66,9 @@ WORKLOADS = {
 STRONG_BH_SHARD = ("cfg3_b16_n8192_causal", "cfg5_heads_n131072_causal")
 DEFAULT_WORKLOAD = "cfg2_n8192_causal"
 NOMINAL_FP16_TFLOPS = 2250.0
+L2_BYTES = 126e6
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of OUR kernel, from the committed `ncu --set full` capture
+NCU_CAPTURES = {"cfg2_n8192_causal": "r01_v4c_causal_n8192_summary.txt"}
 
 
 def flops(B, H, N, D, causal):
@@ -69,7 +87,7 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons through NVML while a timed region runs."""
 
     def __init__(self, index):
         self.samples, self.reasons = [], set()
@@ -111,6 +129,7 @@ class ClockSampler:
         if self.nv:
             self._thr = threading.Thread(target=self._loop, daemon=True)
             self._thr.start()
+        return self
 
     def stop(self):
         self._stop.set()
@@ -127,20 +146,18 @@ class ClockSampler:
 
 
 def ncu_traffic(workload_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-    capture of this workload's kernel (profiles/), or None when no capture of it is committed."""
-    captures = {"cfg2_n8192_causal": "r01_v4c_causal_n8192_summary.txt"}
-    f = captures.get(workload_name)
+    """(bytes, source file) of the committed `ncu --set full` capture of this workload's kernel, or (None, None)."""
+    f = NCU_CAPTURES.get(workload_name)
     if not f:
-        return None
+        return None, None
     try:
         tot = 0.0
         for line in open(os.path.join(REPO, "profiles", f)):
             if line.startswith("dram__bytes_read.sum [Mbyte]") or line.startswith("dram__bytes_write.sum [Mbyte]"):
                 tot += float(line.split("=")[1]) * 1e6
-        return tot or None
+        return (tot or None), "profiles/" + f
     except OSError:
-        return None
+        return None, None
 
 
 def cpu_baseline(workload, budget_rows=None):
@@ -175,51 +192,135 @@ def cpu_baseline(workload, budget_rows=None):
                       f"causal={causal}), {row_flops / 1e9:.1f} GFLOP in {dt:.1f} s; oracle/attn_oracle.c, pthreads"}
 
 
-def bench_ring(args, workload, rank, world, local_rank, barrier):
-    """Config 5: causal N=131072 with ring context parallelism (K/V chunk pairs rotate over NCCL
-    send/recv, overlapped with compute).  world == 1 runs the monolithic kernel as the baseline."""
+# ------------------------------------------------------------------------------------------------
+# context parallelism (config 5) -- data, timing and the in-run parity check
+# ------------------------------------------------------------------------------------------------
+CP_SEED = 4242
+
+
+def cp_chunk(kind, chunk, B, H, C, D, heads=None):
+    """Chunk `chunk` (of 2P) of Q (kind 0), K (1) or V (2) of the global sequence: U(-0.5, 0.5) from a generator
+    keyed by (kind, chunk) alone, so every rank -- and the parity check on rank 0 -- can regenerate any chunk."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(CP_SEED + 3 * chunk + kind)
+    t = (torch.rand((B, H, C, D), device="cuda", generator=g) - 0.5).half()
+    return t if heads is None else t[:, heads].contiguous()
+
+
+def cp_setup(workload, rank, world, local_rank, exchange):
+    """This rank's zig-zag share of the global Q, K, V.  pull: K/V are generated straight into the peer-readable block."""
+    import torch
+    from flash_attention_cuda_b200 import ring
+    B, H, N, D, causal = workload
+    C = N // (2 * world)
+    mine = ring.zigzag_chunks(rank, world)
+    q = [cp_chunk(0, c, B, H, C, D) for c in mine]
+    if exchange == "pull":
+        px = ring.peer_kv(B, H, C, D, torch.device("cuda", local_rank))
+        for slot, c in enumerate(mine):
+            px.k[slot].copy_(cp_chunk(1, c, B, H, C, D))
+            px.v[slot].copy_(cp_chunk(2, c, B, H, C, D))
+        k, v = px.k, px.v
+    else:
+        k = [cp_chunk(1, c, B, H, C, D) for c in mine]
+        v = [cp_chunk(2, c, B, H, C, D) for c in mine]
+    return q, k, v
+
+
+def cp_time(workload, rank, world, local_rank, exchange, steps, warm, barrier, max_over_ranks):
+    """ms per context-parallel forward (max over ranks) and the last step's output chunks."""
+    import torch
+    from flash_attention_cuda_b200 import ring
+    causal = workload[4]
+    q, k, v = cp_setup(workload, rank, world, local_rank, exchange)
+    out = None
+    for _ in range(warm):
+        out = ring.ring_attention_forward(q, k, v, bool(causal), exchange=exchange)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = ring.ring_attention_forward(q, k, v, bool(causal), exchange=exchange)
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1) / steps), out
+
+
+def cp_parity(workload, rank, world, outs):
+    """Sampled output rows of every rank's two chunks against the CPU oracle on the regenerated global sequence.
+    `outs`: {exchange: [o_lo, o_hi]} of this rank.  Returns (on rank 0) {exchange: {max_abs, mean_abs}, ...}."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from flash_attention_cuda_b200 import ring
+    B, H, N, D, causal = workload
+    C = N // (2 * world)
+    heads = [0, H - 1] if H > 1 else [0]
+    offs = sorted({0, 1, C // 2 - 1, C // 2, C - 2, C - 1})
+    mine = ring.zigzag_chunks(rank, world)
+    names = sorted(outs)
+    # [exchange][slot][head][off] rows of this rank -> one small tensor, gathered on every rank
+    sample = torch.stack([torch.stack([outs[n][slot][0, heads][:, offs] for slot in range(2)]) for n in names])
+    gathered = [torch.empty_like(sample) for _ in range(world)]
+    dist.all_gather(gathered, sample.contiguous())
+    if rank != 0:
+        return None
+    import _oracle
+    # the global K, V (sampled heads only) and the sampled Q rows, regenerated chunk by chunk
+    hk = np.empty((1, len(heads), N, D), np.float16)
+    hv = np.empty((1, len(heads), N, D), np.float16)
+    hq = np.zeros((1, len(heads), N, D), np.float16)
+    for c in range(2 * world):
+        hk[0, :, c * C:(c + 1) * C] = cp_chunk(1, c, B, H, C, D, heads)[0].cpu().numpy()
+        hv[0, :, c * C:(c + 1) * C] = cp_chunk(2, c, B, H, C, D, heads)[0].cpu().numpy()
+        hq[0, :, c * C:(c + 1) * C] = cp_chunk(0, c, B, H, C, D, heads)[0].cpu().numpy()
+    bhs, rows = [], []
+    for r in range(world):
+        for c in ring.zigzag_chunks(r, world):
+            for hi in range(len(heads)):
+                for o in offs:
+                    bhs.append(hi)
+                    rows.append(c * C + o)
+    t0 = time.perf_counter()
+    ref = _oracle.attention_rows(hq, hk, hv, causal, np.array(bhs, np.int32), np.array(rows, np.int32))
+    dt = time.perf_counter() - t0
+    res = {"rows_checked": len(rows), "heads": heads, "oracle_s": round(dt, 2),
+           "gate": {"max_abs": _oracle.MAX_ABS_TOL, "mean_abs": _oracle.MEAN_ABS_TOL}, "pass": True}
+    for ni, n in enumerate(names):
+        got = torch.stack([g[ni] for g in gathered]).reshape(-1, D).cpu().numpy()   # rank, slot, head, off: the order above
+        mx, mean = _oracle.diff(got, ref)
+        ok = bool(mx <= _oracle.MAX_ABS_TOL and mean <= _oracle.MEAN_ABS_TOL)
+        res[n] = {"max_abs": mx, "mean_abs": mean, "pass": ok}
+        res["pass"] = res["pass"] and ok
+    return res
+
+
+def bench_ring(args, workload, rank, world, local_rank, barrier, max_over_ranks):
+    """`--workload cfg5_ring_n131072_causal` on its own: context parallelism with --ring-exchange.
+    world == 1 runs the monolithic kernel as the baseline."""
     import torch
     import torch.distributed as dist
     import flash_attention_cuda_b200 as fa
     from flash_attention_cuda_b200 import ring
     B, H, N, D, causal = workload
-    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    steps, warm = max(2, min(args.steps, 5)), 3
     C = N // (2 * world)
-
-    def mk(n):
-        return (torch.rand((B, H, n, D), device="cuda", generator=g) - 0.5).half()
-
     if world == 1:
-        q, k, v = mk(N), mk(N), mk(N)
+        g = torch.Generator(device="cuda").manual_seed(1234)
+        q, k, v = ((torch.rand((B, H, N, D), device="cuda", generator=g) - 0.5).half() for _ in range(3))
         o = torch.empty_like(q)
-        step = lambda: fa.flash_attn_fwd(q, k, v, causal=bool(causal), out=o)
+        for _ in range(warm):
+            fa.flash_attn_fwd(q, k, v, causal=bool(causal), out=o)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fa.flash_attn_fwd(q, k, v, causal=bool(causal), out=o)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
     else:
-        exchange = args.ring_exchange
-        q = [mk(C), mk(C)]
-        if exchange == "pull":
-            # K/V live in peer-readable memory from the start (no staging copy inside the step)
-            px = ring.peer_kv(B, H, C, D, torch.device("cuda", local_rank))
-            for t in px.k + px.v:
-                t.copy_(mk(C))
-            k, v = px.k, px.v
-        else:
-            k, v = [mk(C), mk(C)], [mk(C), mk(C)]
-        step = lambda: ring.ring_attention_forward(q, k, v, bool(causal), exchange=exchange)
-    steps, warm = max(2, min(args.steps, 5)), 2
-    for _ in range(warm):
-        step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / steps
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, _ = cp_time(workload, rank, world, local_rank, args.ring_exchange, steps, warm, barrier, max_over_ranks)
     if rank == 0:
         fl = flops(B, H, N, D, causal)
         pk = peaks()
@@ -256,6 +357,12 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="also print the README-style TFLOPS table to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
+    ap.add_argument("--sustain-s", type=float, default=2.0,
+                    help="seconds of back-to-back launches for the `sustained` sub-record (0 = skip)")
+    ap.add_argument("--flush-l2", action="store_true",
+                    help="write a 256 MiB buffer between timed launches (cold L2); automatic when the tensors fit L2")
+    ap.add_argument("--hot-l2", action="store_true", help="never flush: the reference's method (FA.cu:942-960)")
+    ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the strong_cfg3 / cp_cfg5 / cp_parity legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -278,7 +385,6 @@ def main():
                 "e2e": {"value": cb["value"], "unit": "TFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -293,6 +399,13 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return float(x)
 
     # ---- implementations: a launcher taking device pointers + a stream, like FA.cu:606-611 ----
     if args.impl == "ours":
@@ -327,7 +440,7 @@ def main():
     sp = ctypes.c_void_p(stream.cuda_stream)
 
     if args.workload.startswith("cfg5_ring"):
-        return bench_ring(args, workload, rank, world, local_rank, barrier)
+        return bench_ring(args, workload, rank, world, local_rank, barrier, max_over_ranks)
     if args.workload in STRONG_BH_SHARD and world > 1:
         # strong scaling: the B*H heads are split across ranks (no collective), total work fixed
         from flash_attention_cuda_b200.ring import bh_shard
@@ -340,40 +453,74 @@ def main():
         q, k, v = ((torch.rand((b, h, n, d), device="cuda", generator=g) - 0.5).half() for _ in range(3))
         return q, k, v, torch.empty_like(q)
 
-    def time_kernel(b, h, n, d, c, steps, warmup):
-        q, k, v, o = make_inputs(b, h, n, d, n)
+    flush_buf = [None]
+
+    def time_kernel(b, h, n, d, c, steps, warmup, flush=False, bufs=None, active=True):
+        """ms per launch (max over ranks).  flush: a 256 MiB write between launches evicts the tensors from L2; every
+        launch is then timed by its own event pair so that the flush is outside the timed intervals."""
+        if not active:           # this rank sits the leg out (single-GPU baselines inside a multi-GPU run)
+            barrier(); barrier()
+            return max_over_ranks(0.0), None
+        q, k, v, o = bufs or make_inputs(b, h, n, d, n)
         for _ in range(warmup):
             launch(q, k, v, o, b, h, n, d, c, sp)
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            launch(q, k, v, o, b, h, n, d, c, sp)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1) / steps
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, (q, k, v, o)
+        if not flush:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                launch(q, k, v, o, b, h, n, d, c, sp)
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1) / steps
+        else:
+            if flush_buf[0] is None:
+                flush_buf[0] = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for a, z in ev:
+                flush_buf[0].fill_(1)
+                a.record(stream)
+                launch(q, k, v, o, b, h, n, d, c, sp)
+                z.record(stream)
+            barrier()
+            ms = sum(a.elapsed_time(z) for a, z in ev) / steps
+        return max_over_ranks(ms), (q, k, v, o)
 
     # ---- main timed region, with clocks sampled while it runs ----
-    sampler = ClockSampler(local_rank)
+    nbytes = B * H * N * D * 2
+    fits_l2 = 4 * nbytes <= L2_BYTES
+    flush = (args.flush_l2 or fits_l2) and not args.hot_l2
+    sampler = ClockSampler(local_rank).start()
     l0 = launches_of()
-    # untimed warm-up happens inside time_kernel; sample clocks only around the whole call
-    sampler.start()
-    ms, bufs = time_kernel(B, H, N, D, causal, args.steps, args.warmup)
+    ms, bufs = time_kernel(B, H, N, D, causal, args.steps, args.warmup, flush=flush)
     clocks = sampler.stop()
     launches = launches_of() - l0 - args.warmup
     fl = flops(B, H, N, D, causal)
     tflops_rank = fl / (ms * 1e-3) / 1e12
     value = tflops_rank * n_gpus if world > 1 else tflops_rank
+    hot_ms = None
+    if flush:      # the reference's method (back-to-back launches, tensors L2-resident) next to the cold-L2 number
+        hot_ms, _ = time_kernel(B, H, N, D, causal, args.steps, 3, flush=False, bufs=bufs)
+
+    # ---- sustained leg: seconds of back-to-back launches, its own clocks record ----
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(args.steps, int(args.sustain_s * 1e3 / ms) + 1)
+        s2 = ClockSampler(local_rank).start()
+        sus_ms, _ = time_kernel(B, H, N, D, causal, n_sus, 3, flush=False, bufs=bufs)
+        c2 = s2.stop()
+        pk0 = peaks()
+        sus_tf = fl / (sus_ms * 1e-3) / 1e12
+        sustained = {"value": round(sus_tf * (n_gpus if world > 1 else 1), 2), "unit": "TFLOPS", "steps": n_sus,
+                     "ms_per_step": round(sus_ms, 5), "seconds": round(n_sus * sus_ms * 1e-3, 2), "clocks": c2,
+                     "roofline": {"bound": "tensor", "achieved": round(sus_tf, 2),
+                                  "peak": pk0["tflops_sustained"] or None, "unit": "TFLOP/s",
+                                  "frac": round(sus_tf / pk0["tflops_sustained"], 4) if pk0["tflops_sustained"] else None,
+                                  "peak_source": pk0["source"] + ", cuBLAS bf16 sustained (4 s back to back)"}}
 
     # ---- e2e: host buffers through the public call, H2D + kernel + D2H timed every step ----
     e2e_steps = args.e2e_steps or min(args.steps, 20)
     q, k, v, o = bufs
-    nbytes = q.numel() * 2
     hq, hk, hv = (torch.empty(q.shape, dtype=torch.float16).pin_memory() for _ in range(3))
     ho = torch.empty(q.shape, dtype=torch.float16).pin_memory()
     hq.copy_(q.cpu()); hk.copy_(k.cpu()); hv.copy_(v.cpu())
@@ -388,29 +535,101 @@ def main():
             launch(q, k, v, o, B, H, N, D, causal, sp)
             ho.copy_(o, non_blocking=True)
             stream.synchronize()
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+
+    def wall_ms(step, n):
+        for _ in range(2):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step()
+        barrier()
+        return max_over_ranks((time.perf_counter() - t0) * 1e3 / n)
+
+    e2e_ms = wall_ms(e2e_step, e2e_steps)
     e2e_val = fl / (e2e_ms * 1e-3) / 1e12 * (n_gpus if world > 1 else 1)
+    # the floor of that call: the same bytes over PCIe (H2D of Q, K, V on one stream, D2H of O on another -- full duplex),
+    # no kernel, every rank at once.  With several ranks the host's memory system is shared: this is what e2e can reach.
+    side = torch.cuda.Stream()
+
+    def copy_only():
+        q.copy_(hq, non_blocking=True); k.copy_(hk, non_blocking=True); v.copy_(hv, non_blocking=True)
+        with torch.cuda.stream(side):
+            ho.copy_(o, non_blocking=True)
+        stream.synchronize()
+        side.synchronize()
+    copy_ms = wall_ms(copy_only, max(3, e2e_steps // 2))
 
     # ---- optional README-style sweep (stderr, rank 0) ----
     sweep = None
-    if args.sweep and rank == 0:
+    if args.sweep and world == 1:
         sweep = {}
         for c in (0, 1):
             for n in (512, 768, 1024, 2048, 4096, 8192, 16384):
-                m, _ = time_kernel(1, 32, n, 128, c, 50, 5)
+                cold = 4 * 32 * n * 128 * 2 <= L2_BYTES
+                m, _ = time_kernel(1, 32, n, 128, c, 50, 5, flush=cold and not args.hot_l2)
                 sweep[f"{'causal' if c else 'full'}_{n}"] = round(flops(1, 32, n, 128, c) / (m * 1e-3) / 1e12, 1)
-        print("sweep TFLOPS (B1 H32 D128):", json.dumps(sweep), file=sys.stderr)
+        print("sweep TFLOPS (B1 H32 D128; cold L2 where the tensors fit L2):", json.dumps(sweep), file=sys.stderr)
+
+    # ---- N > 1: the two multi-GPU configurations BASELINE.json names, in the same process group ----
+    multi = {}
+    parity_ok = True
+    if world > 1 and args.impl == "ours" and not args.no_multi and args.workload == DEFAULT_WORKLOAD:
+        from flash_attention_cuda_b200 import ring
+        del q, k, v, o, hq, hk, hv, ho, bufs
+        torch.cuda.empty_cache()
+        pk0 = peaks()
+        # -- config 3: B16 H32 N8192 causal, heads split over the ranks, no collective
+        B3, H3, N3, D3, c3 = WORKLOADS["cfg3_b16_n8192_causal"]
+        _, cnt = ring.bh_shard(B3 * H3, rank, world)
+        fl3 = flops(B3, H3, N3, D3, c3)
+        st3 = max(5, min(args.steps, 30))
+        ms3, b3 = time_kernel(1, cnt, N3, D3, c3, st3, 3)
+        # the same slice on ONE GPU with the others idle: same launch length, same power regime
+        ms3_slice, _ = time_kernel(1, cnt, N3, D3, c3, st3, 3, bufs=b3, active=(rank == 0))
+        del b3
+        torch.cuda.empty_cache()
+        # and the whole batch on one GPU (a launch `world` times longer: power-capped clocks)
+        ms3_full, b3f = time_kernel(1, B3 * H3, N3, D3, c3, max(3, st3 // 4), 2, active=(rank == 0))
+        del b3f
+        torch.cuda.empty_cache()
+        multi["strong_cfg3"] = {
+            "workload": "cfg3_b16_n8192_causal", "heads_per_rank": cnt, "steps": st3, "ms": round(ms3, 4),
+            "tflops": round(fl3 / (ms3 * 1e-3) / 1e12, 1),
+            "one_gpu_same_slice_ms": round(ms3_slice, 4), "efficiency": round(ms3_slice / ms3, 4),
+            "one_gpu_whole_batch_ms": round(ms3_full, 4),
+            "efficiency_vs_whole_batch_on_one_gpu": round(ms3_full / (world * ms3), 4),
+            "note": "efficiency = time of one rank's slice alone on one GPU / time with all ranks running theirs "
+                    "(same launch length on both sides); the whole-batch figure is a launch N times longer and runs "
+                    "at power-capped clocks"}
+        # -- config 5: B1 H32 N131072 causal: heads split (no communication) vs context parallel
+        w5 = WORKLOADS["cfg5_ring_n131072_causal"]
+        B5, H5, N5, D5, c5 = w5
+        fl5 = flops(*w5)
+        _, cnt5 = ring.bh_shard(B5 * H5, rank, world)
+        ms5_heads, b5 = time_kernel(1, cnt5, N5, D5, c5, 3, 2)
+        del b5
+        torch.cuda.empty_cache()
+        cp = {"workload": "cfg5_ring_n131072_causal", "chunk_rows": N5 // (2 * world),
+              "heads_split_bound": {"ms": round(ms5_heads, 3), "tflops": round(fl5 / (ms5_heads * 1e-3) / 1e12, 1),
+                                    "heads_per_rank": cnt5}}
+        outs = {}
+        for ex in ("pull", "sendrecv"):
+            ms5, out = cp_time(w5, rank, world, local_rank, ex, 4, 3, barrier, max_over_ranks)
+            outs[ex] = [t.clone() for t in out]
+            cp[ex] = {"ms": round(ms5, 3), "tflops": round(fl5 / (ms5 * 1e-3) / 1e12, 1),
+                      "efficiency": round(ms5_heads / ms5, 4),
+                      "frac_of_sustained_peak_per_gpu": round(fl5 / (ms5 * 1e-3) / 1e12 / world / pk0["tflops_sustained"], 4)
+                      if pk0["tflops_sustained"] else None}
+        cp["note"] = ("efficiency = heads-split time (same shape, no communication, measured in this run) / context-parallel "
+                      "time; pull = copy-engine reads of the owners' K/V chunks over NVLink, sendrecv = NCCL ring")
+        multi["cp_cfg5"] = cp
+        par = cp_parity(w5, rank, world, outs)
+        if rank == 0:
+            multi["cp_parity"] = par
+            parity_ok = bool(par["pass"])
+        del outs
+        ring.release_peer_kv()
 
     if rank != 0:
         if world > 1:
@@ -418,6 +637,7 @@ def main():
         return
 
     pk = peaks()
+    traffic, traffic_src = ncu_traffic(args.workload) if args.impl == "ours" else (None, None)
     out = {
         "metric": "fwd_tflops", "value": round(value, 2), "unit": "TFLOPS", "n_gpus": n_gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
@@ -427,26 +647,36 @@ def main():
                    "per_gpu": "every rank runs the full workload on its own GPU (batch x heads shard, no collective)"
                               if not (args.workload in STRONG_BH_SHARD and world > 1) else
                               "the workload's B*H heads are split across the ranks (no collective); B,H here are rank 0's share",
-                   "l2": f"inputs {4 * nbytes / 2**20:.0f} MiB per step > 126 MB L2 (no flush needed)"
-                         if 4 * nbytes > 126e6 else "inputs fit L2: hot-L2 timing, reference method (FA.cu:942-960)",
+                   "l2": (f"inputs {4 * nbytes / 2**20:.0f} MiB per step > 126 MB L2 (no flush needed)" if not fits_l2 else
+                          "inputs fit L2: a 256 MiB write between launches evicts them (cold L2), every launch timed by its "
+                          "own event pair; `hot_l2_ms_per_step` is the reference's method (FA.cu:942-960)" if flush else
+                          "inputs fit L2: hot-L2 timing, reference method (FA.cu:942-960)"),
                    "flops_convention": "4*B*H*N^2*D, /2 causal (FA.cu:938-939)"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_val, 3), "unit": "TFLOPS", "h2d_bytes_per_step": 3 * nbytes,
                 "d2h_bytes_per_step": nbytes, "ms_per_step": round(e2e_ms, 4), "steps": e2e_steps,
+                "copy_only_ms": round(copy_ms, 4),
+                "copy_only_gbs_per_rank": round(4 * nbytes / (copy_ms * 1e-3) / 1e9, 1),
+                "frac_of_copy_floor": round(copy_ms / e2e_ms, 4),
                 "call": "flash_attn_fwd_host (pinned host Q,K,V -> device, kernel, O -> pinned host; 8 head chunks "
                         "pipelined over three streams, every byte still crosses PCIe inside the timed region)"
                         if args.impl == "ours" else "H2D x3 + flash_attention_v9_dispatch + D2H (FA.cu:774-780)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": round(tflops_rank, 2), "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": round(tflops_rank / pk["tflops"], 4), "traffic": ncu_traffic(args.workload),
-                     "peak_source": pk["source"] + ", cuBLAS bf16 burst",
-                     "frac_of_sustained": round(tflops_rank / pk["tflops_sustained"], 4) if pk["tflops_sustained"] else None,
+                     "frac": round(tflops_rank / pk["tflops"], 4), "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": pk["source"] + ", cuBLAS bf16 burst (timed region of milliseconds)",
                      "frac_of_nominal_2250": round(tflops_rank / NOMINAL_FP16_TFLOPS, 4),
                      "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 4 * nbytes,
                      "hbm_gbs_algorithmic": round(4 * nbytes / (ms * 1e-3) / 1e9, 1)},
     }
+    if hot_ms is not None:
+        out["hot_l2_ms_per_step"] = round(hot_ms, 5)
+        out["hot_l2_tflops"] = round(fl / (hot_ms * 1e-3) / 1e12, 2)
+    if sustained:
+        out["sustained"] = sustained
     if sweep:
         out["sweep_tflops"] = sweep
+    out.update(multi)
     if args.impl != "ours":
         out["impl"] = "reference"
         out["reference_kind"] = "V9 kernel (flash_attention_v9_dispatch) rebuilt for sm_100a, unmodified source"
@@ -455,6 +685,8 @@ def main():
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if not parity_ok:
+        raise SystemExit("cp_parity FAILED: context-parallel output differs from the CPU oracle beyond 2e-3 / 2e-4")
 
 
 if __name__ == "__main__":

@@ -22,6 +22,15 @@ constexpr int kSchedSlots = 4096;
 constexpr int kHostChunks = 32;    // most head chunks flash_attn_fwd_host can pipeline over PCIe (events are per chunk)
 constexpr int kHostChunksDefault = 8;   // FLASH_ATTN_B200_HOST_CHUNKS overrides (A/B runs)
 constexpr int kGroupMB = 32;       // K+V bytes of one scheduling group of heads (make_params)
+// exp2 on the FMA pipe (fa::poly_pair): share of element pairs for D = 128 with >= 32 KV tiles / for D = 64.
+// Build-time so that A/B variants are one -D away; the defaults are the measured optimum (profiles/).
+#ifndef FA_POLY_LONG
+#define FA_POLY_LONG 1
+#endif
+#ifndef FA_POLY_D64
+#define FA_POLY_D64 0
+#endif
+constexpr int kPolyLong = FA_POLY_LONG, kPolyD64 = FA_POLY_D64;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -109,12 +118,12 @@ DeviceState* device_state(int* err) {
         st->num_sms = prop.multiProcessorCount;
         st->cc_major = prop.major;
         if (prop.major != 10) { st->ok = FA_ERR_UNSUPPORTED_ARCH; return; }
-        int r = set_kernel_attrs<128, 1>();
+        int r = set_kernel_attrs<128, kPolyLong>();
         if (r == 0) r = set_kernel_attrs<128, 0>();
-        if (r == 0) r = set_kernel_attrs<64, 0>();
-        if (r == 0) r = set_kernel_attrs<128, 1, true>();
+        if (r == 0) r = set_kernel_attrs<64, kPolyD64>();
+        if (r == 0) r = set_kernel_attrs<128, kPolyLong, true>();
         if (r == 0) r = set_kernel_attrs<128, 0, true>();
-        if (r == 0) r = set_kernel_attrs<64, 0, true>();
+        if (r == 0) r = set_kernel_attrs<64, kPolyD64, true>();
         if (r == 0 && use_pair_kernel()) {
             r = set_pair_kernel_attrs<128, 1>();
             if (r == 0) r = set_pair_kernel_attrs<128, 2>();
@@ -298,12 +307,12 @@ int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaS
     // O store map (unused in partial mode: describe Q's extent on a valid pointer)
     if ((rc = make_tmap(&to, p.o ? (const void*)p.o : q, p.BH, p.Nq, D, fa::kBlockN, bf16)) != FA_OK) return rc;
     if (bf16) {
-        if (D == 64) return launch<64, 0, true>(st, tq, tk, tv, to, p, stream);
-        return use_poly(D, p.Nkv) ? launch<128, 1, true>(st, tq, tk, tv, to, p, stream)
+        if (D == 64) return launch<64, kPolyD64, true>(st, tq, tk, tv, to, p, stream);
+        return use_poly(D, p.Nkv) ? launch<128, kPolyLong, true>(st, tq, tk, tv, to, p, stream)
                                   : launch<128, 0, true>(st, tq, tk, tv, to, p, stream);
     }
-    if (D == 64) return launch<64, 0>(st, tq, tk, tv, to, p, stream);
-    return use_poly(D, p.Nkv) ? launch<128, 1>(st, tq, tk, tv, to, p, stream) : launch<128, 0>(st, tq, tk, tv, to, p, stream);
+    if (D == 64) return launch<64, kPolyD64>(st, tq, tk, tv, to, p, stream);
+    return use_poly(D, p.Nkv) ? launch<128, kPolyLong>(st, tq, tk, tv, to, p, stream) : launch<128, 0>(st, tq, tk, tv, to, p, stream);
 }
 
 }  // namespace
@@ -444,8 +453,8 @@ int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_att
     if (B < 1 || H < 1 || N < 1) return FA_ERR_BAD_SHAPE;
     memset(info, 0, sizeof *info);
     cudaFuncAttributes attr;
-    cudaError_t e = D == 64            ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<64, 0>)
-                    : use_poly(D, N) ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, 1>)
+    cudaError_t e = D == 64            ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<64, kPolyD64>)
+                    : use_poly(D, N) ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, kPolyLong>)
                                      : cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, 0>);
     if (e != cudaSuccess) return (int)e;
     int err = 0;

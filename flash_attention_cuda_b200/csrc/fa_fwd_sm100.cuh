@@ -42,7 +42,9 @@
 //   -DFA_SUM_GUARD     softmax without a row max, guarded by the row sum (r01_v4c_sumguard_experiment.txt)
 //   -DFA_SCHED_FENCE   data-dependency fence that makes ptxas store the first piece of P before the second
 //                      piece's exponentials (r01_accumulate_race.txt)
-//   -DFA_STREAM_S      second half of S re-read from TMEM instead of held in registers (r01_softmax_schedule.txt; not yet run)
+//   -DFA_STREAM        streamed softmax (softmax_tile_stream: S read in chunks, exponentials against the row's current
+//                      reference, lazy rescale at the end of the tile): parity-clean, 1 % slower (r02_stream_experiment.txt)
+//   -DFA_STREAM_S      second half of S re-read from TMEM instead of held in registers (r01_softmax_schedule.txt)
 //   -DFA_SINGLE_TILE_MODE  one Q tile per work item, selected at run time by FLASH_ATTN_B200_ITEM_TILES=1 (not yet run)
 //   -DFA_P_PARTS=3     P in three pieces;  -DFA_REGS_SOFTMAX / -DFA_REGS_OTHER  setmaxnreg budgets
 //                      (r01_v4b_defer_group_ab.log)
@@ -263,28 +265,29 @@ __device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Which element pairs take exp2 on the FMA pipe: kPoly = 0 none, 1 one pair in 4, 2 two in 4, 3 three in 8
+__host__ __device__ constexpr bool poly_pair(int kPoly, int pair) {
+    return kPoly == 3 ? (pair % 8 == 0 || pair % 8 == 3 || pair % 8 == 6) : (pair % 4) < kPoly;
+}
 // exponentials + fp16 packing of kCols consecutive columns (64 = one half of the tile)
 template <int kPoly, bool kBF16, int kCols = 64>
 __device__ __forceinline__ void exp_half(const uint32_t* s, uint32_t* pk, uint64_t scale2, uint64_t neg2,
                                          uint64_t& sum_a, uint64_t& sum_b) {
 #pragma unroll
-    for (int i = 0; i < kCols; i += 8) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int e = i + 2 * q;
-            const uint64_t x2 =
-                fma_f32x2(pack_f32x2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, neg2);
-            float p0, p1;
+    for (int e = 0; e < kCols; e += 2) {
+        const int q = e / 2;                                           // element pair
+        const uint64_t x2 =
+            fma_f32x2(pack_f32x2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, neg2);
+        float p0, p1;
 #ifdef FA_SKELETON
-            unpack_f32x2(x2, p0, p1);
+        unpack_f32x2(x2, p0, p1);
 #else
-            if (q < kPoly) exp2_pair<true>(x2, p0, p1);
-            else exp2_pair<false>(x2, p0, p1);
+        if (poly_pair(kPoly, q)) exp2_pair<true>(x2, p0, p1);
+        else exp2_pair<false>(x2, p0, p1);
 #endif
-            if (q & 1) sum_b = add_f32x2(sum_b, pack_f32x2(p0, p1));   // row sum of the un-rounded p (FA.cu:273-279)
-            else sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
-            pk[e / 2] = pack_16x2<kBF16>(p0, p1);                      // low half = even column
-        }
+        if (q & 1) sum_b = add_f32x2(sum_b, pack_f32x2(p0, p1));       // row sum of the un-rounded p (FA.cu:273-279)
+        else sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
+        pk[q] = pack_16x2<kBF16>(p0, p1);                              // low half = even column
     }
 }
 
@@ -580,6 +583,125 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     l_run += a0 + a1;
 }
 #endif  // FA_SUM_GUARD
+
+// ---- streamed softmax of one 128x128 S tile (one thread per row) ----
+// softmax_tile above cannot start an exponential before all 128 columns of the row have crossed the TMEM read
+// port (64 B/clk per sub-partition: 256 cycles per warp and tile) and the 61-deep max has run -- ~400 cycles of
+// the S -> P -> PV -> QK^T chain during which the SFU idles.  Here S is read in four chunks of 32 columns and the
+// exponentials of a chunk run against the reference max the row ALREADY has (first tile of an item: the max of
+// chunk 0), under the loads and the max of the following chunks:
+//   * P may exceed 1 by up to 2^kHardThreshold (fp16/bf16 hold 2^15 with full relative precision, l and O are fp32);
+//     only a row whose scores outgrow the reference by more than that makes the warp drop the tile's work and
+//     redo it with softmax_tile (nothing has been written to TMEM at that point: the vote sits before the
+//     first tcgen05.st);
+//   * the lazy update of the reference (threshold 2^kRescaleThreshold, as above) moves to the END of the tile:
+//     O is rescaled behind this tile's PV, while the tensor core runs the tile's next QK^T -- off the chain.
+constexpr float kHardThreshold = 15.0f;
+
+template <bool kMask>
+__device__ __forceinline__ void mask_chunk(uint32_t* c, int base, int lim_local) {
+    if (kMask) {
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+            if (base + i >= lim_local) c[i] = 0xff800000u;  // -inf
+    }
+}
+__device__ __forceinline__ float max_chunk(const uint32_t* c) {
+    float m0 = fmax3(__uint_as_float(c[0]), __uint_as_float(c[1]), __uint_as_float(c[2]));
+    float m1 = fmax3(__uint_as_float(c[3]), __uint_as_float(c[4]), __uint_as_float(c[5]));
+    float m2 = fmax3(__uint_as_float(c[6]), __uint_as_float(c[7]), __uint_as_float(c[8]));
+    float m3 = fmax3(__uint_as_float(c[9]), __uint_as_float(c[10]), __uint_as_float(c[11]));
+    m0 = fmax3(m0, __uint_as_float(c[12]), __uint_as_float(c[13]));
+    m1 = fmax3(m1, __uint_as_float(c[14]), __uint_as_float(c[15]));
+    m2 = fmax3(m2, __uint_as_float(c[16]), __uint_as_float(c[17]));
+    m3 = fmax3(m3, __uint_as_float(c[18]), __uint_as_float(c[19]));
+    m0 = fmax3(m0, __uint_as_float(c[20]), __uint_as_float(c[21]));
+    m1 = fmax3(m1, __uint_as_float(c[22]), __uint_as_float(c[23]));
+    m2 = fmax3(m2, __uint_as_float(c[24]), __uint_as_float(c[25]));
+    m3 = fmax3(m3, __uint_as_float(c[26]), __uint_as_float(c[27]));
+    m0 = fmax3(m0, __uint_as_float(c[28]), __uint_as_float(c[29]));
+    m1 = fmax3(m1, __uint_as_float(c[30]), __uint_as_float(c[31]));
+    return fmaxf(fmax3(m0, m1, m2), m3);
+}
+
+// Returns false (and leaves TMEM, m_ref, l_run untouched) when the tile has to be redone by softmax_tile.
+template <int D, bool kMask, int kPoly, bool kBF16>
+__device__ __forceinline__ bool softmax_tile_stream(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
+                                                    uint32_t bar_o_full, int lim_local, bool last, uint32_t pv_count,
+                                                    float& m_ref, float& l_run) {
+    static_assert(kPParts == 2, "the streamed softmax delivers P in two pieces");
+    uint32_t a[32], b[32], c[32];
+    tmem_ld_x32(tS, a);
+    tmem_wait_ld();
+    tmem_ld_x32(tS + 32, b);                   // lands under chunk 0's max and exponentials
+    mask_chunk<kMask>(a, 0, lim_local);
+    const float mx0 = max_chunk(a);
+    // reference for this tile: the row's current one; a row without one (first tile) takes the max of chunk 0
+    const float m_use = (m_ref == -INFINITY) ? mx0 : m_ref;
+    const float neg = -((m_use == -INFINITY) ? 0.0f : m_use) * p.scale_log2;
+    const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+    const uint64_t neg2 = pack_f32x2(neg, neg);
+    uint64_t sum_a = 0ull, sum_b = 0ull;
+    uint32_t pk[32], pk2[32];
+    exp_half<kPoly, kBF16, 32>(a, pk, scale2, neg2, sum_a, sum_b);
+    tmem_wait_ld();
+    tmem_ld_x32(tS + 64, a);                   // chunks 2 and 3 land under chunk 1
+    tmem_ld_x32(tS + 96, c);
+    mask_chunk<kMask>(b, 32, lim_local);
+    const float mx1 = max_chunk(b);
+    exp_half<kPoly, kBF16, 32>(b, pk + 16, scale2, neg2, sum_a, sum_b);
+    tmem_wait_ld();
+    mask_chunk<kMask>(a, 64, lim_local);
+    mask_chunk<kMask>(c, 96, lim_local);
+    const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(max_chunk(a), max_chunk(c)));
+    // the exponentials above (and below) are only good if nothing outgrew the reference by more than 2^kHard
+    const bool bad = (m_tile - m_use) * p.scale_log2 > kHardThreshold;    // NaN (-inf - -inf) -> false
+    if (__any_sync(0xffffffffu, bad)) return false;
+
+    auto publish = [&](int part) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(bar_p_full + 8 * part);   // one arrival per warp (barrier count 4)
+    };
+    tmem_st_x32(tS, pk);                       // piece 0: keys 0-63 -> columns [0,32) (all of S is in registers)
+    exp_half<kPoly, kBF16, 32>(a, pk2, scale2, neg2, sum_a, sum_b);
+    publish(0);
+    exp_half<kPoly, kBF16, 32>(c, pk2 + 16, scale2, neg2, sum_a, sum_b);
+    tmem_st_x32(tS + 32, pk2);                 // piece 1: keys 64-127 -> columns [32,64)
+    publish(1);
+    float a0, a1;
+    unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
+    l_run += a0 + a1;
+    m_ref = m_use;
+
+    // Lazy rescale for the NEXT tile (replaces the reference's every-tile O *= alpha, FA.cu:267-270)
+    const float m_new = fmaxf(m_use, m_tile);
+    const bool need = (m_new - m_use) * p.scale_log2 > kRescaleThreshold;
+    if (!last && __any_sync(0xffffffffu, need)) {
+        const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_use - m_new) * p.scale_log2);
+        mbar_wait(bar_o_full, pv_count & 1u, 42);          // PV of THIS tile retired: O_t is quiescent
+        tc_fence_after();
+        const uint64_t alpha2 = pack_f32x2(alpha, alpha);
+#pragma unroll 1
+        for (int cc = 0; cc < D; cc += 32) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + cc, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                float lo, hi;
+                unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), lo, hi);
+                o[i] = __float_as_uint(lo);
+                o[i + 1] = __float_as_uint(hi);
+            }
+            tmem_st_x32(tO + cc, o);
+        }
+        l_run *= alpha;
+        m_ref = m_new;
+    }
+    return true;
+}
 
 template <int D, int kPoly, bool kBF16 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -925,10 +1047,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #endif
                 const int k0 = j * kBlockN;
                 const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
+#if !defined(FA_STREAM) || defined(FA_SUM_GUARD)
                 if (need_mask)
                     softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, lim - k0, j > 0, pv_count, m_ref, l_run);
                 else
                     softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, kBlockN, j > 0, pv_count, m_ref, l_run);
+#else
+                // streamed softmax; a tile whose scores outgrew the reference max by more than 2^15 (warp vote)
+                // is redone by the classic form, which takes the whole row's max first
+                const bool last = j + 1 == n_t;
+                const bool done = need_mask
+                    ? softmax_tile_stream<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, lim - k0, last, pv_count, m_ref, l_run)
+                    : softmax_tile_stream<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, kBlockN, last, pv_count, m_ref, l_run);
+                if (!done)
+                    softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half,
+                                                        need_mask ? lim - k0 : kBlockN, j > 0, pv_count, m_ref, l_run);
+#endif
                 ++pv_count;
 #ifdef FA_TIMING
                 if (lane == 0 && (warp & 3) == 0 && j > 0 && (j & 7) == 0) {   // sampled: 1 tile in 8

@@ -102,7 +102,12 @@ def test_increasing_scores_force_rescale_every_tile(fa):
         gate(gpu_attention(fa, q, k, v, causal), _oracle.attention(q, k, v, causal))
 
 
-@pytest.mark.parametrize("D,step_at,jump", [(128, 64, 12.0), (128, 0, 12.0), (64, 64, 20.0), (128, 96, 30.0)])
+@pytest.mark.parametrize("D,step_at,jump", [(128, 64, 12.0), (128, 0, 12.0), (64, 64, 20.0), (128, 96, 30.0),
+                                            # streamed softmax: 7 nats = 2^10.1 (between the lazy threshold 2^8 and the hard
+                                            # one 2^15: reference moves at the end of the tile), 4 nats = 2^5.8 (moves every
+                                            # second tile), 11 nats = 2^15.9 (just past the hard threshold: tile redone)
+                                            (128, 32, 7.0), (128, 100, 7.0), (64, 0, 7.0), (128, 64, 4.0), (128, 40, 11.0),
+                                            (128, 127, 10.3), (64, 33, 10.5)])
 def test_score_steps_at_half_tile_boundaries(fa, D, step_at, jump):
     """Scaled scores are flat and then jump by `jump` nats every 128 keys, at key 128*t + step_at: with step_at = 64
     the second half of every KV tile outgrows whatever reference the first half was exponentiated against (an O
