@@ -6,7 +6,7 @@ NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 PKG       := flash_attention_cuda_b200
 LIB       := $(PKG)/libflashattn_b200.so
 CSRC      := $(PKG)/csrc/fa_api.cu
-CHDR      := $(PKG)/csrc/fa_fwd_sm100.cuh $(PKG)/csrc/fa_fwd_pair_sm100.cuh $(PKG)/csrc/sm100_ptx.cuh include/flash_attn.h
+CHDR      := $(PKG)/csrc/fa_fwd_sm100.cuh $(PKG)/csrc/sm100_ptx.cuh include/flash_attn.h
 
 all: $(LIB) oracle flash_attention
 
@@ -17,8 +17,8 @@ oracle:
 	$(MAKE) -C oracle
 
 # harness: links the product library; loads the checkers (oracle/) with dlopen at run time
-flash_attention: tests/harness/flash_attention_cli.cu $(LIB) include/flash_attn.h
-	$(NVCC) $(NVCCFLAGS) -Iinclude tests/harness/flash_attention_cli.cu -o $@ -L$(PKG) -lflashattn_b200 \
+flash_attention: cli/flash_attention_cli.cu $(LIB) include/flash_attn.h
+	$(NVCC) $(NVCCFLAGS) -Iinclude cli/flash_attention_cli.cu -o $@ -L$(PKG) -lflashattn_b200 \
 	    -Xlinker -rpath -Xlinker '$$ORIGIN/$(PKG)' -ldl
 
 ptxas-info:

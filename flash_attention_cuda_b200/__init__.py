@@ -29,6 +29,7 @@ ERRORS = {
     -5: "FA_ERR_UNSUPPORTED_ARCH",
     -6: "FA_ERR_TENSORMAP",
     -7: "FA_ERR_WORKSPACE",
+    -8: "FA_ERR_WATCHDOG",
 }
 
 # every symbol include/flash_attn.h declares
@@ -46,6 +47,7 @@ EXPORTED_SYMBOLS = (
     "flash_attn_peer_close",
     "flash_attn_peer_free",
     "flash_attn_peer_copy",
+    "flash_attn_status",
     "flash_attn_launch_count",
     "flash_attn_destroy",
     "flash_attn_error_string",
@@ -67,8 +69,7 @@ class KernelInfo(ctypes.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_PKG_DIR, "csrc", f) for f in ("fa_api.cu", "fa_fwd_sm100.cuh", "fa_fwd_pair_sm100.cuh",
-                                                       "sm100_ptx.cuh")]
+    srcs = [os.path.join(_PKG_DIR, "csrc", f) for f in ("fa_api.cu", "fa_fwd_sm100.cuh", "sm100_ptx.cuh")]
     srcs.append(os.path.join(_REPO, "include", "flash_attn.h"))
     if not force and os.path.exists(LIB_PATH):
         if all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs if os.path.exists(s)):
@@ -136,6 +137,11 @@ def lib() -> ctypes.CDLL:
         L.flash_attn_debug_tiles_per_item.restype = ci
     L.flash_attn_debug_status.argtypes = [ctypes.POINTER(ctypes.c_uint)]
     L.flash_attn_debug_status.restype = ci
+    if hasattr(L, "flash_attn_status"):   # absent from archived A/B builds of older kernels
+        L.flash_attn_status.argtypes = [ctypes.POINTER(ctypes.c_uint)]
+        L.flash_attn_status.restype = ci
+        L.flash_attn_debug_trip_watchdog.argtypes = [ctypes.c_uint, vp]
+        L.flash_attn_debug_trip_watchdog.restype = ci
     _lib = L
     return L
 
@@ -151,25 +157,48 @@ def _stream_ptr(stream=None):
     return ctypes.c_void_p(s.cuda_stream)
 
 
+def _check_qkv(q, k, v, dtypes, what):
+    """The data contract of the C ABI (include/flash_attn.h): CUDA, one 16-bit type, contiguous [B, H, N, D], one device."""
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise ValueError(f"{what} needs CUDA tensors (there is no CPU path)")
+    if q.dtype not in dtypes or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise TypeError(f"{what} takes {' or '.join(str(d).replace('torch.', '') for d in dtypes)} tensors, all of one type")
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4 or k.shape != v.shape:
+        raise ValueError("q must be [B, H, Nq, D] and k, v [B, H, Nkv, D]")
+    if q.shape[:2] != k.shape[:2] or q.shape[3] != k.shape[3]:
+        raise ValueError("q, k, v must agree in B, H and D")
+    if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+        raise ValueError("q, k, v must be contiguous [B, H, N, D] (a slice along N is not)")
+    if k.device != q.device or v.device != q.device:
+        raise ValueError("q, k, v must live on one device")
+
+
+def _check_f32(t, shape, name, device):
+    import torch
+    if not t.is_cuda or t.device != device:
+        raise ValueError(f"{name} must be a CUDA tensor on {device}")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise TypeError(f"{name} must be contiguous float32")
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, not {tuple(t.shape)}")
+
+
 def flash_attn_fwd(q, k, v, causal: bool = True, out=None, stream=None):
     """O = softmax(Q K^T / sqrt(D) [+ causal mask]) V for FP16 (or BF16) CUDA tensors [B, H, N, D].
 
     Same contract as the reference dispatcher (flash_attention.cu:606-663); enqueues on the
     current (or given) torch stream and returns the output tensor without synchronising."""
     import torch
-    if not (q.is_cuda and k.is_cuda and v.is_cuda):
-        raise ValueError("flash_attn_fwd needs CUDA tensors (there is no CPU path)")
-    if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype or v.dtype != q.dtype:
-        raise TypeError("flash_attn_fwd takes float16 (or bfloat16) tensors, all of one type")
-    if q.dim() != 4 or q.shape != k.shape or q.shape != v.shape:
+    _check_qkv(q, k, v, (torch.float16, torch.bfloat16), "flash_attn_fwd")
+    if q.shape != k.shape:
         raise ValueError("q, k, v must all be [B, H, N, D]")
-    if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
-        raise ValueError("q, k, v must be contiguous [B, H, N, D]")
     B, H, N, D = q.shape
     if out is None:
         out = torch.empty_like(q)
     if out.dtype != q.dtype:
         raise TypeError("out must have the dtype of q, k, v")
+    if out.shape != q.shape or out.device != q.device or not out.is_contiguous():
+        raise ValueError("out must be a contiguous [B, H, N, D] tensor on the device of q")
     entry = lib().flash_attn_fwd if q.dtype == torch.float16 else lib().flash_attn_fwd_bf16
     with torch.cuda.device(q.device):
         rc = entry(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
@@ -180,10 +209,16 @@ def flash_attn_fwd(q, k, v, causal: bool = True, out=None, stream=None):
 
 def flash_attn_fwd_partial(q, k, v, o_partial, ml, causal: bool, q_offset: int, kv_offset: int,
                            accumulate: bool, stream=None):
-    """One K/V block of a longer sequence -> (o_partial fp32, ml) partial state (include/flash_attn.h)."""
+    """One K/V block of a longer sequence -> (o_partial fp32, ml) partial state (include/flash_attn.h).
+    FP16 only: the partial / merge path has no BF16 instantiation."""
+    import torch
+    _check_qkv(q, k, v, (torch.float16,), "flash_attn_fwd_partial")
     B, H, Nq, D = q.shape
     Nkv = k.shape[2]
-    import torch
+    if o_partial.numel() != B * H * Nq * D or ml.numel() != B * H * Nq * 2:
+        raise ValueError("o_partial must hold B*H*Nq*D and ml B*H*Nq*2 float32 values")
+    _check_f32(o_partial, o_partial.shape, "o_partial", q.device)
+    _check_f32(ml, ml.shape, "ml", q.device)
     with torch.cuda.device(q.device):
         rc = lib().flash_attn_fwd_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), o_partial.data_ptr(),
                                      ml.data_ptr(), B, H, Nq, Nkv, D, 1 if causal else 0,
@@ -191,12 +226,25 @@ def flash_attn_fwd_partial(q, k, v, o_partial, ml, causal: bool, q_offset: int, 
     check(rc)
 
 
+def _check_f16_out(out, rows, D, name="out"):
+    import torch
+    if not out.is_cuda or out.dtype != torch.float16 or not out.is_contiguous():
+        raise TypeError(f"{name} must be a contiguous float16 CUDA tensor (the merge writes FP16)")
+    if out.numel() != rows * D:
+        raise ValueError(f"{name} must hold rows * D = {rows * D} elements, not {out.numel()}")
+
+
 def flash_attn_finalize(o_partial, ml, out, stream=None):
     import torch
-    rows = o_partial.numel() // o_partial.shape[-1]
+    D = o_partial.shape[-1]
+    rows = o_partial.numel() // D
+    _check_f32(o_partial, o_partial.shape, "o_partial", out.device)
+    _check_f32(ml, ml.shape, "ml", out.device)
+    if ml.numel() != rows * 2:
+        raise ValueError("ml must hold rows * 2 float32 values")
+    _check_f16_out(out, rows, D)
     with torch.cuda.device(out.device):
-        rc = lib().flash_attn_finalize(o_partial.data_ptr(), ml.data_ptr(), out.data_ptr(), rows,
-                                       o_partial.shape[-1], _stream_ptr(stream))
+        rc = lib().flash_attn_finalize(o_partial.data_ptr(), ml.data_ptr(), out.data_ptr(), rows, D, _stream_ptr(stream))
     check(rc)
     return out
 
@@ -204,8 +252,12 @@ def flash_attn_finalize(o_partial, ml, out, stream=None):
 def flash_attn_merge(o_partials, mls, out, stream=None):
     """Merge `splits` partial states (o_partials [S, rows, D] fp32, mls [S, rows, 2]) into the FP16 tensor `out`."""
     import torch
+    if o_partials.dim() != 3:
+        raise ValueError("o_partials must be [splits, rows, D]")
     S, rows, D = o_partials.shape
-    assert mls.shape == (S, rows, 2) and o_partials.is_contiguous() and mls.is_contiguous()
+    _check_f32(o_partials, (S, rows, D), "o_partials", out.device)
+    _check_f32(mls, (S, rows, 2), "mls", out.device)
+    _check_f16_out(out, rows, D)
     with torch.cuda.device(out.device):
         rc = lib().flash_attn_merge(o_partials.data_ptr(), mls.data_ptr(), out.data_ptr(), S, rows, D,
                                     _stream_ptr(stream))
@@ -219,10 +271,12 @@ def kernel_info(B: int, H: int, N: int, D: int, causal: bool) -> dict:
     return {n: getattr(info, n) for n, _ in KernelInfo._fields_}
 
 
-def watchdog_status() -> dict:
-    """Synchronises and returns the kernel watchdog record (aborted == 0 on a healthy run)."""
+def watchdog_status(sync: bool = True) -> dict:
+    """The kernel watchdog record of the current device (include/flash_attn.h: flash_attn_status), by default after
+    a device synchronise.  aborted == 1: a kernel gave up on a barrier and the next call will raise FA_ERR_WATCHDOG."""
     buf = (ctypes.c_uint * 4)()
-    check(lib().flash_attn_debug_status(buf))
+    L = lib()
+    check((L.flash_attn_debug_status if sync or not hasattr(L, "flash_attn_status") else L.flash_attn_status)(buf))
     return {"aborted": int(buf[0]), "tag": int(buf[1]), "block": int(buf[2]), "thread": int(buf[3])}
 
 
@@ -293,5 +347,5 @@ def work_item(w: int, B: int, H: int, Nq: int, Nkv: int, D: int, causal: bool, s
 
 
 def tiles_per_item(D: int) -> int:
-    """128-row Q tiles one work item covers (2 for the default kernel; 1 or 2 for the pair kernel)."""
+    """128-row Q tiles one work item covers (2; 1 in single-tile mode)."""
     return int(lib().flash_attn_debug_tiles_per_item(D))

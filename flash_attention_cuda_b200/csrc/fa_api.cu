@@ -12,8 +12,7 @@
 #include <cstring>
 #include <mutex>
 
-#include "fa_fwd_sm100.cuh"        // default kernel: one CTA per work item, two Q tiles per CTA
-#include "fa_fwd_pair_sm100.cuh"   // experimental CTA-pair kernel (cta_group::2), opt-in
+#include "fa_fwd_sm100.cuh"        // the kernel: one CTA per work item, two Q tiles per CTA
 
 namespace {
 
@@ -42,15 +41,37 @@ std::atomic<int> g_sm_margin{0};     // SMs the persistent grid leaves free (fla
 std::once_flag g_encode_once;
 EncodeTiledFn g_encode = nullptr;
 
+constexpr int kCaptureSlots = 1024;  // scheduler words reserved for launches recorded into CUDA graphs (one each, never reused)
+constexpr int kTmapCache = 8;        // cached descriptor sets per device (flash_attn_fwd re-encodes nothing for a repeated call)
+
+struct TmapSet {
+    const void *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr;
+    int BH = 0, Nq = 0, Nkv = 0, D = 0, bf16 = 0;
+    unsigned long long stamp = 0;    // 0 = empty; otherwise the LRU clock of its last use
+    CUtensorMap tq, tk, tv, to;
+};
+
 struct DeviceState {
-    std::once_flag once;
+    std::mutex init_mu;
+    bool inited = false;
     int ok = 0;           // cudaSuccess when attributes are set
     int num_sms = 0;
     int cc_major = 0;
-    // dynamic tile scheduler state: kSchedSlots x {next, done} ints, zero when idle; a launch uses
-    // slot (sequence number % kSchedSlots) and its last CTA re-zeroes it
+    // dynamic tile scheduler state: {next, done} int pairs, zero when idle.  An eager launch uses pair
+    // (sequence number % kSchedSlots) and its last CTA re-zeroes it; a launch recorded into a CUDA graph gets
+    // a pair of its own behind those (a replay may run next to eager launches that wrapped around to any
+    // of the shared pairs, and next to other graphs)
     int* sched = nullptr;
     std::atomic<unsigned> sched_seq{0};
+    std::atomic<int> capture_seq{0};
+    // kernel watchdog record {aborted, tag, block, thread} in zero-copy host memory: the kernel writes it, the
+    // launcher reads it at the start of every call without synchronising (sm100_ptx.cuh)
+    unsigned int* wd_host = nullptr;
+    unsigned int wd_last[4] = {0, 0, 0, 0};
+    // descriptor cache
+    std::mutex tmap_mu;
+    TmapSet tmaps[kTmapCache];
+    unsigned long long tmap_clock = 0;
     // staging buffers for flash_attn_fwd_host
     std::mutex host_mu;
     void* stage = nullptr;
@@ -77,64 +98,63 @@ int set_kernel_attrs() {
 }
 // exp2 on the FMA pipe for 1 pair in 4 only where it pays: D = 128 and at least 32 KV tiles (fa_fwd_sm100.cuh)
 bool use_poly(int D, int Nkv) { return D == 128 && Nkv >= 4096; }
-template <int D, int CG>
-int set_pair_kernel_attrs() {
-    return (int)cudaFuncSetAttribute(fa_pair::fa_fwd_kernel<D, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     fa_pair::Cfg<D, CG>::kSmemBytes);
-}
-
-// FLASH_ATTN_B200_KERNEL=pair selects the experimental CTA-pair kernel for the whole
-// process; anything else runs the default kernel.  Read once.
-bool use_pair_kernel() {
-    static const bool pair = []() {
-        const char* e = getenv("FLASH_ATTN_B200_KERNEL");
-        return e && strcmp(e, "pair") == 0;
-    }();
-    return pair;
-}
-// CTAs per work unit of the pair kernel: D = 128 runs as CTA pairs (tcgen05.mma.cta_group::2, M = 256);
-// D = 64 keeps one CTA per unit (its V half would be narrower than a 128-byte swizzle panel).
-// FLASH_ATTN_B200_CG=1 forces single CTAs for D = 128 as well (A/B measurements).
-int pair_cta_group_for(int D) {
-    static const int forced = []() {
-        const char* e = getenv("FLASH_ATTN_B200_CG");
-        return (e && e[0] == '1') ? 1 : 0;
-    }();
-    return (D == 64 || forced == 1) ? 1 : 2;
-}
-
-// Per-device one-time setup.  Re-entrant from several host threads (one per GPU in the
-// multi-GPU harness): everything is guarded by the device's once_flag.
+// Per-device setup, on the first call on that device (and again after flash_attn_destroy).  Re-entrant from
+// several host threads (one per GPU in a multi-GPU harness): guarded by the device's mutex.
 DeviceState* device_state(int* err) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { *err = (int)e; return nullptr; }
     if (dev < 0 || dev >= kMaxDevices) { *err = FA_ERR_UNSUPPORTED_ARCH; return nullptr; }
     DeviceState* st = &g_dev[dev];
-    std::call_once(st->once, [st, dev]() {
-        cudaDeviceProp prop;
-        cudaError_t e2 = cudaGetDeviceProperties(&prop, dev);
-        if (e2 != cudaSuccess) { st->ok = (int)e2; return; }
-        st->num_sms = prop.multiProcessorCount;
-        st->cc_major = prop.major;
-        if (prop.major != 10) { st->ok = FA_ERR_UNSUPPORTED_ARCH; return; }
-        int r = set_kernel_attrs<128, kPolyLong>();
-        if (r == 0) r = set_kernel_attrs<128, 0>();
-        if (r == 0) r = set_kernel_attrs<64, kPolyD64>();
-        if (r == 0) r = set_kernel_attrs<128, kPolyLong, true>();
-        if (r == 0) r = set_kernel_attrs<128, 0, true>();
-        if (r == 0) r = set_kernel_attrs<64, kPolyD64, true>();
-        if (r == 0 && use_pair_kernel()) {
-            r = set_pair_kernel_attrs<128, 1>();
-            if (r == 0) r = set_pair_kernel_attrs<128, 2>();
-            if (r == 0) r = set_pair_kernel_attrs<64, 1>();
-        }
-        if (r == 0) r = (int)cudaMalloc(&st->sched, kSchedSlots * 2 * sizeof(int));
-        if (r == 0) r = (int)cudaMemset(st->sched, 0, kSchedSlots * 2 * sizeof(int));
-        st->ok = r;
-    });
+    std::lock_guard<std::mutex> lock(st->init_mu);
+    if (!st->inited) {
+        st->inited = true;
+        st->ok = [st, dev]() -> int {
+            cudaDeviceProp prop;
+            cudaError_t e2 = cudaGetDeviceProperties(&prop, dev);
+            if (e2 != cudaSuccess) return (int)e2;
+            st->num_sms = prop.multiProcessorCount;
+            st->cc_major = prop.major;
+            if (prop.major != 10) return FA_ERR_UNSUPPORTED_ARCH;
+            int r = set_kernel_attrs<128, kPolyLong>();
+            if (r == 0) r = set_kernel_attrs<128, 0>();
+            if (r == 0) r = set_kernel_attrs<64, kPolyD64>();
+            if (r == 0) r = set_kernel_attrs<128, kPolyLong, true>();
+            if (r == 0) r = set_kernel_attrs<128, 0, true>();
+            if (r == 0) r = set_kernel_attrs<64, kPolyD64, true>();
+            const size_t sched_bytes = (size_t)(kSchedSlots + kCaptureSlots) * 2 * sizeof(int);
+            if (r == 0) r = (int)cudaMalloc(&st->sched, sched_bytes);
+            if (r == 0) r = (int)cudaMemset(st->sched, 0, sched_bytes);
+            // watchdog mirror: 4 words of mapped, pinned host memory; the kernel gets its device alias through a symbol
+            if (r == 0) r = (int)cudaHostAlloc(reinterpret_cast<void**>(&st->wd_host), 4 * sizeof(unsigned int), cudaHostAllocMapped);
+            if (r == 0) {
+                memset(st->wd_host, 0, 4 * sizeof(unsigned int));
+                unsigned int* dalias = nullptr;
+                r = (int)cudaHostGetDevicePointer(reinterpret_cast<void**>(&dalias), st->wd_host, 0);
+                if (r == 0) r = (int)cudaMemcpyToSymbol(sm100::g_watchdog_host, &dalias, sizeof dalias);
+                const unsigned int z[4] = {0, 0, 0, 0};
+                if (r == 0) r = (int)cudaMemcpyToSymbol(sm100::g_watchdog, z, sizeof z);
+            }
+            return r;
+        }();
+    }
     if (st->ok != 0) { *err = st->ok; return nullptr; }
     return st;
+}
+
+// A kernel whose mbarrier protocol timed out (sm100_ptx.cuh) has drained with garbage results and left a record.
+// It is reported ONCE, as FA_ERR_WATCHDOG from the next call on that device, and then cleared, so that one bad launch
+// (or a legitimate wait stretched past the timeout by a debugger / time-slicing) does not poison the process.
+int take_watchdog(DeviceState* st) {
+    if (!st->wd_host || *reinterpret_cast<volatile unsigned int*>(st->wd_host) == 0u) return FA_OK;
+    cudaDeviceSynchronize();      // everything queued behind the aborted launch has drained as well
+    for (int i = 0; i < 4; i++) st->wd_last[i] = reinterpret_cast<volatile unsigned int*>(st->wd_host)[i];
+    const unsigned int z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(sm100::g_watchdog, z, sizeof z);
+    memset(st->wd_host, 0, 4 * sizeof(unsigned int));
+    // scheduler words of the aborted launches may be mid-count
+    cudaMemset(st->sched, 0, (size_t)(kSchedSlots + kCaptureSlots) * 2 * sizeof(int));
+    return FA_ERR_WATCHDOG;
 }
 
 // [BH, N, D] fp16, box = 64 halves x `rows` rows x 1 head, 128-byte swizzle; rows past N read as zero
@@ -212,7 +232,16 @@ int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const 
     if (avail < 1) avail = 1;
     int grid = p.total_work < avail ? p.total_work : avail;
     if (grid < 1) grid = 1;
-    p.sched = st->sched + 2 * (st->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusNone;
+    if (cap == cudaStreamCaptureStatusActive) {
+        // the pair is baked into the graph: give it one nobody else will ever count on
+        const int c = st->capture_seq.fetch_add(1, std::memory_order_relaxed);
+        if (c >= kCaptureSlots) return FA_ERR_WORKSPACE;
+        p.sched = st->sched + 2 * (kSchedSlots + c);
+    } else {
+        p.sched = st->sched + 2 * (st->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+    }
     // launched with programmatic stream serialization (PDL): the kernel's prologue overlaps the tail
     // of its predecessor in the stream; it executes griddepcontrol.wait before touching global memory
     cudaLaunchConfig_t cfg;
@@ -232,87 +261,59 @@ int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const 
     return (int)cudaGetLastError();   // FA.cu:662
 }
 
-// ---- experimental CTA-pair kernel (fa_fwd_pair_sm100.cuh) ----
-fa_pair::Params make_pair_params(const fa::Params& b, int D) {
-    fa_pair::Params p;
-    memset(&p, 0, sizeof p);
-    p.o = b.o; p.o_partial = b.o_partial; p.ml = b.ml;
-    p.Nq = b.Nq; p.Nkv = b.Nkv; p.BH = b.BH;
-    p.causal = b.causal; p.shift = b.shift;
-    p.cg = pair_cta_group_for(D);
-    p.nqu = (b.Nq + p.cg * fa_pair::kBlockM - 1) / (p.cg * fa_pair::kBlockM);
-    p.total_work = (int)((long long)b.BH * p.nqu);
-    p.group_heads = b.group_heads;
-    p.partial_mode = b.partial_mode; p.accumulate = b.accumulate;
-    p.scale = b.scale; p.scale_log2 = b.scale_log2;
-    return p;
-}
-
-template <int D, int CG>
-int launch_pair(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                const CUtensorMap& to, fa_pair::Params p, cudaStream_t stream) {
-    int avail = (st->num_sms - g_sm_margin.load(std::memory_order_relaxed)) / CG;
-    if (avail < 1) avail = 1;
-    int units = p.total_work < avail ? p.total_work : avail;
-    if (units < 1) units = 1;
-    p.sched = st->sched + 2 * (st->sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)(units * CG));
-    cfg.blockDim = dim3(fa_pair::kNumThreads);
-    cfg.dynamicSmemBytes = fa_pair::Cfg<D, CG>::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = CG;
-    attr[1].val.clusterDim.y = 1;
-    attr[1].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = CG == 2 ? 2 : 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, fa_pair::fa_fwd_kernel<D, CG>, tq, tk, tv, to, p);
-    if (le != cudaSuccess) return (int)le;
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return (int)cudaGetLastError();
-}
-
-int run_pair(DeviceState* st, const void* q, const void* k, const void* v, const fa::Params& base, int D,
-             cudaStream_t stream) {
-    fa_pair::Params p = make_pair_params(base, D);
-    if ((long long)p.BH * p.nqu > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
-    CUtensorMap tq, tk, tv, to;
+// The four descriptors of a call (Q, K, V loads, O store), from the device's cache when the same pointers and shape
+// were seen before: cuTensorMapEncodeTiled x 4 is most of the host time of a launch, and short sequences
+// (BASELINE config 1: ~20 us of GPU time) are called in loops on the same buffers.
+int get_tmaps(DeviceState* st, const void* q, const void* k, const void* v, const void* o, const fa::Params& p, int D,
+              bool bf16, TmapSet* out) {
+    {
+        std::lock_guard<std::mutex> lock(st->tmap_mu);
+        for (TmapSet& c : st->tmaps)
+            if (c.stamp && c.q == q && c.k == k && c.v == v && c.o == o && c.BH == p.BH && c.Nq == p.Nq && c.Nkv == p.Nkv &&
+                c.D == D && c.bf16 == (int)bf16) {
+                c.stamp = ++st->tmap_clock;
+                *out = c;
+                return FA_OK;
+            }
+    }
+    TmapSet t;
+    t.q = q; t.k = k; t.v = v; t.o = o;
+    t.BH = p.BH; t.Nq = p.Nq; t.Nkv = p.Nkv; t.D = D; t.bf16 = (int)bf16;
     int rc;
-    if ((rc = make_tmap(&tq, q, p.BH, p.Nq, D)) != FA_OK) return rc;
-    if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D, fa_pair::kBlockN / p.cg)) != FA_OK) return rc;
-    if ((rc = make_tmap(&tv, v, p.BH, p.Nkv, D)) != FA_OK) return rc;
+    if ((rc = make_tmap(&t.tq, q, p.BH, p.Nq, D, fa::kBlockN, bf16)) != FA_OK) return rc;
+    if ((rc = make_tmap(&t.tk, k, p.BH, p.Nkv, D, fa::kBlockN, bf16)) != FA_OK) return rc;
+    if ((rc = make_tmap(&t.tv, v, p.BH, p.Nkv, D, fa::kBlockN, bf16)) != FA_OK) return rc;
     // O store map (unused in partial mode: describe Q's extent on a valid pointer)
-    if ((rc = make_tmap(&to, p.o ? (const void*)p.o : q, p.BH, p.Nq, D)) != FA_OK) return rc;
-    if (D == 64) return launch_pair<64, 1>(st, tq, tk, tv, to, p, stream);
-    return p.cg == 2 ? launch_pair<128, 2>(st, tq, tk, tv, to, p, stream)
-                     : launch_pair<128, 1>(st, tq, tk, tv, to, p, stream);
+    if ((rc = make_tmap(&t.to, o ? o : q, p.BH, p.Nq, D, fa::kBlockN, bf16)) != FA_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lock(st->tmap_mu);
+        TmapSet* victim = &st->tmaps[0];
+        for (TmapSet& c : st->tmaps)
+            if (c.stamp < victim->stamp) victim = &c;
+        t.stamp = ++st->tmap_clock;
+        *victim = t;
+    }
+    *out = t;
+    return FA_OK;
 }
 
 int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaStream_t stream, bool bf16 = false) {
     int err = 0;
     DeviceState* st = device_state(&err);
     if (!st) return err;
-    if (use_pair_kernel() && !bf16) return run_pair(st, q, k, v, p, D, stream);   // the experimental kernel is FP16 only
+    if ((err = take_watchdog(st)) != FA_OK) return err;
     if ((long long)p.BH * p.nqp > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
-    CUtensorMap tq, tk, tv, to;
-    int rc;
-    if ((rc = make_tmap(&tq, q, p.BH, p.Nq, D, fa::kBlockN, bf16)) != FA_OK) return rc;
-    if ((rc = make_tmap(&tk, k, p.BH, p.Nkv, D, fa::kBlockN, bf16)) != FA_OK) return rc;
-    if ((rc = make_tmap(&tv, v, p.BH, p.Nkv, D, fa::kBlockN, bf16)) != FA_OK) return rc;
-    // O store map (unused in partial mode: describe Q's extent on a valid pointer)
-    if ((rc = make_tmap(&to, p.o ? (const void*)p.o : q, p.BH, p.Nq, D, fa::kBlockN, bf16)) != FA_OK) return rc;
+    TmapSet t;
+    int rc = get_tmaps(st, q, k, v, p.partial_mode ? nullptr : (const void*)p.o, p, D, bf16, &t);
+    if (rc != FA_OK) return rc;
     if (bf16) {
-        if (D == 64) return launch<64, kPolyD64, true>(st, tq, tk, tv, to, p, stream);
-        return use_poly(D, p.Nkv) ? launch<128, kPolyLong, true>(st, tq, tk, tv, to, p, stream)
-                                  : launch<128, 0, true>(st, tq, tk, tv, to, p, stream);
+        if (D == 64) return launch<64, kPolyD64, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
+        return use_poly(D, p.Nkv) ? launch<128, kPolyLong, true>(st, t.tq, t.tk, t.tv, t.to, p, stream)
+                                  : launch<128, 0, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
     }
-    if (D == 64) return launch<64, kPolyD64>(st, tq, tk, tv, to, p, stream);
-    return use_poly(D, p.Nkv) ? launch<128, kPolyLong>(st, tq, tk, tv, to, p, stream) : launch<128, 0>(st, tq, tk, tv, to, p, stream);
+    if (D == 64) return launch<64, kPolyD64>(st, t.tq, t.tk, t.tv, t.to, p, stream);
+    return use_poly(D, p.Nkv) ? launch<128, kPolyLong>(st, t.tq, t.tk, t.tv, t.to, p, stream)
+                              : launch<128, 0>(st, t.tq, t.tk, t.tv, t.to, p, stream);
 }
 
 }  // namespace
@@ -380,44 +381,21 @@ int flash_attn_merge(const float* o_partial, const float* ml, void* o, int split
     return (int)cudaGetLastError();
 }
 
-int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho, int B, int H, int N, int D,
-                        int causal) {
-    if (!hq || !hk || !hv || !ho) return FA_ERR_NULL_PTR;
-    if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
-    if (B < 1 || H < 1 || N < 1) return FA_ERR_BAD_SHAPE;
-    int err = 0;
-    DeviceState* st = device_state(&err);
-    if (!st) return err;
-    const size_t bytes = (size_t)B * H * N * D * sizeof(__half);
-    std::lock_guard<std::mutex> lock(st->host_mu);
+// Body of flash_attn_fwd_host once the streams, events and the staging buffer exist.
+static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const void* hv, void* ho, int BH, int N, int D,
+                         int causal, size_t bytes) {
     cudaError_t e;
-    if (!st->host_ready) {
-        if ((e = cudaStreamCreateWithFlags(&st->host_stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-        if ((e = cudaStreamCreateWithFlags(&st->host_in, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-        if ((e = cudaStreamCreateWithFlags(&st->host_out, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-        for (int i = 0; i < kHostChunks; i++) {
-            if ((e = cudaEventCreateWithFlags(&st->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-            if ((e = cudaEventCreateWithFlags(&st->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-        }
-        st->host_ready = true;
-    }
-    if (st->stage_bytes < 4 * bytes) {
-        if (st->stage) cudaFree(st->stage);
-        st->stage = nullptr;
-        st->stage_bytes = 0;
-        if ((e = cudaMalloc(&st->stage, 4 * bytes)) != cudaSuccess) return (int)e;
-        st->stage_bytes = 4 * bytes;
-    }
     char* base = static_cast<char*>(st->stage);
     char *dq = base, *dk = base + bytes, *dv = base + 2 * bytes, *dout = base + 3 * bytes;
     // The reference copies everything in, dispatches, copies everything out (FA.cu:774-780).  Heads are
     // independent, so the same work is cut into head chunks and pipelined: while chunk c computes,
     // chunk c+1 is on its way in and chunk c-1 on its way out (PCIe is full duplex; three streams,
     // one event pair per chunk).  The wire time of Q, K, V dominates; kernels and O hide under it.
-    const int BH = B * H;
+    // The overlap needs PINNED host buffers (cudaHostAlloc / cudaHostRegister): with pageable memory every
+    // cudaMemcpyAsync stages through the driver's bounce buffer and blocks this thread, chunk by chunk.
     static const int want_chunks = [] {
-        const char* e = getenv("FLASH_ATTN_B200_HOST_CHUNKS");
-        const int v = e ? atoi(e) : 0;
+        const char* env = getenv("FLASH_ATTN_B200_HOST_CHUNKS");
+        const int v = env ? atoi(env) : 0;
         return v >= 1 && v <= kHostChunks ? v : kHostChunksDefault;
     }();
     const int chunks = BH < want_chunks ? BH : want_chunks;
@@ -446,6 +424,47 @@ int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho
     return (int)cudaStreamSynchronize(st->host_out);
 }
 
+int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho, int B, int H, int N, int D,
+                        int causal) {
+    if (!hq || !hk || !hv || !ho) return FA_ERR_NULL_PTR;
+    if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+    if (B < 1 || H < 1 || N < 1) return FA_ERR_BAD_SHAPE;
+    if ((long long)B * H > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
+    int err = 0;
+    DeviceState* st = device_state(&err);
+    if (!st) return err;
+    const size_t bytes = (size_t)B * H * N * D * sizeof(__half);
+    std::lock_guard<std::mutex> lock(st->host_mu);
+    cudaError_t e;
+    if (!st->host_ready) {
+        if ((e = cudaStreamCreateWithFlags(&st->host_stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamCreateWithFlags(&st->host_in, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamCreateWithFlags(&st->host_out, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        for (int i = 0; i < kHostChunks; i++) {
+            if ((e = cudaEventCreateWithFlags(&st->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+            if ((e = cudaEventCreateWithFlags(&st->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+        }
+        st->host_ready = true;
+    }
+    if (st->stage_bytes < 4 * bytes) {
+        if (st->stage) cudaFree(st->stage);
+        st->stage = nullptr;
+        st->stage_bytes = 0;
+        if ((e = cudaMalloc(&st->stage, 4 * bytes)) != cudaSuccess) return (int)e;
+        st->stage_bytes = 4 * bytes;
+    }
+    int rc = host_pipeline(st, hq, hk, hv, ho, B * H, N, D, causal, bytes);
+    if (rc != FA_OK) {
+        // an error in the middle of the chunk loop leaves copies and kernels queued on the cached staging buffer
+        // (and on the caller's host memory): nothing may still be in flight when the caller sees the error
+        cudaStreamSynchronize(st->host_in);
+        cudaStreamSynchronize(st->host_stream);
+        cudaStreamSynchronize(st->host_out);
+        return rc;
+    }
+    return take_watchdog(st);   // O is on the host: say so if a kernel of this call gave up on a barrier
+}
+
 int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_attn_kernel_info* info) {
     (void)causal;
     if (!info) return FA_ERR_NULL_PTR;
@@ -460,39 +479,18 @@ int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_att
     int err = 0;
     DeviceState* st = device_state(&err);
     if (!st) return err;
+    if ((long long)B * H > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
     fa::Params p = make_params(B * H, N, N, D, causal, 0);
+    if ((long long)p.BH * p.nqp > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
     info->cta_group = 1;
-    if (use_pair_kernel()) {
-        const int cg = pair_cta_group_for(D);
-        e = D == 64    ? cudaFuncGetAttributes(&attr, fa_pair::fa_fwd_kernel<64, 1>)
-            : cg == 2 ? cudaFuncGetAttributes(&attr, fa_pair::fa_fwd_kernel<128, 2>)
-                      : cudaFuncGetAttributes(&attr, fa_pair::fa_fwd_kernel<128, 1>);
-        if (e != cudaSuccess) return (int)e;
-        const fa_pair::Params pp = make_pair_params(p, D);
-        info->regs_per_thread = attr.numRegs;
-        info->local_bytes_per_thread = (int)attr.localSizeBytes;
-        info->static_smem_bytes = (int)attr.sharedSizeBytes;
-        info->dynamic_smem_bytes = D == 64    ? fa_pair::Cfg<64, 1>::kSmemBytes
-                                   : cg == 2 ? fa_pair::Cfg<128, 2>::kSmemBytes
-                                             : fa_pair::Cfg<128, 1>::kSmemBytes;
-        info->threads_per_cta = fa_pair::kNumThreads;
-        int units = pp.total_work < st->num_sms / cg ? pp.total_work : st->num_sms / cg;
-        info->ctas = (units < 1 ? 1 : units) * cg;
-        info->tmem_columns = fa_pair::kTmemCols;
-        info->kv_stages = D == 64    ? fa_pair::Cfg<64, 1>::kKStages + fa_pair::Cfg<64, 1>::kVStages
-                          : cg == 2 ? fa_pair::Cfg<128, 2>::kKStages + fa_pair::Cfg<128, 2>::kVStages
-                                    : fa_pair::Cfg<128, 1>::kKStages + fa_pair::Cfg<128, 1>::kVStages;
-        info->work_items = pp.total_work;
-        info->num_sms = st->num_sms;
-        info->cta_group = cg;
-        return FA_OK;
-    }
     info->regs_per_thread = attr.numRegs;
     info->local_bytes_per_thread = (int)attr.localSizeBytes;
     info->static_smem_bytes = (int)attr.sharedSizeBytes;
     info->dynamic_smem_bytes = D == 128 ? fa::Cfg<128>::kSmemBytes : fa::Cfg<64>::kSmemBytes;
     info->threads_per_cta = fa::kNumThreads;
-    info->ctas = p.total_work < st->num_sms ? p.total_work : st->num_sms;
+    int avail = st->num_sms - g_sm_margin.load(std::memory_order_relaxed);   // flash_attn_set_sm_margin
+    if (avail < 1) avail = 1;
+    info->ctas = p.total_work < avail ? p.total_work : avail;
     info->tmem_columns = fa::kTmemCols;
     info->kv_stages = D == 128 ? fa::Cfg<128>::kStages : fa::Cfg<64>::kStages;
     info->work_items = p.total_work;
@@ -548,23 +546,37 @@ void flash_attn_destroy(void) {
     if (cudaGetDevice(&saved) != cudaSuccess) return;
     for (int d = 0; d < kMaxDevices; d++) {
         DeviceState* st = &g_dev[d];
+        std::lock_guard<std::mutex> init_lock(st->init_mu);
         std::lock_guard<std::mutex> lock(st->host_mu);
-        if (st->stage || st->host_ready) {
-            cudaSetDevice(d);
-            if (st->stage) cudaFree(st->stage);
-            if (st->host_stream) cudaStreamDestroy(st->host_stream);
-            if (st->host_in) cudaStreamDestroy(st->host_in);
-            if (st->host_out) cudaStreamDestroy(st->host_out);
-            for (int i = 0; i < kHostChunks; i++) {
-                if (st->ev_in[i]) cudaEventDestroy(st->ev_in[i]);
-                if (st->ev_k[i]) cudaEventDestroy(st->ev_k[i]);
-                st->ev_in[i] = st->ev_k[i] = nullptr;
-            }
-            st->stage = nullptr;
-            st->stage_bytes = 0;
-            st->host_stream = st->host_in = st->host_out = nullptr;
-            st->host_ready = false;
+        if (!st->inited) continue;
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+        if (st->stage) cudaFree(st->stage);
+        if (st->host_stream) cudaStreamDestroy(st->host_stream);
+        if (st->host_in) cudaStreamDestroy(st->host_in);
+        if (st->host_out) cudaStreamDestroy(st->host_out);
+        for (int i = 0; i < kHostChunks; i++) {
+            if (st->ev_in[i]) cudaEventDestroy(st->ev_in[i]);
+            if (st->ev_k[i]) cudaEventDestroy(st->ev_k[i]);
+            st->ev_in[i] = st->ev_k[i] = nullptr;
         }
+        st->stage = nullptr;
+        st->stage_bytes = 0;
+        st->host_stream = st->host_in = st->host_out = nullptr;
+        st->host_ready = false;
+        if (st->sched) cudaFree(st->sched);
+        st->sched = nullptr;
+        if (st->wd_host) {
+            unsigned int* none = nullptr;
+            cudaMemcpyToSymbol(sm100::g_watchdog_host, &none, sizeof none);
+            cudaFreeHost(st->wd_host);
+        }
+        st->wd_host = nullptr;
+        {
+            std::lock_guard<std::mutex> tl(st->tmap_mu);
+            for (TmapSet& c : st->tmaps) c.stamp = 0;
+        }
+        st->inited = false;      // the next call on this device sets it up again
     }
     cudaSetDevice(saved);
 }
@@ -579,22 +591,44 @@ const char* flash_attn_error_string(int code) {
         case FA_ERR_UNSUPPORTED_ARCH: return "device is not compute capability 10.x (B200, sm_100a)";
         case FA_ERR_TENSORMAP: return "cuTensorMapEncodeTiled failed or is unavailable";
         case FA_ERR_WORKSPACE: return "workspace missing or too small";
+        case FA_ERR_WATCHDOG: return "an earlier kernel gave up waiting on a barrier and produced garbage (flash_attn_status has the record)";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
 }
 
-const char* flash_attn_version(void) { return use_pair_kernel() ? "flashattn_b200 0.2 (sm_100a tcgen05/TMA forward, experimental CTA-pair kernel)"
-                             : "flashattn_b200 0.2 (sm_100a tcgen05/TMA forward)"; }
+const char* flash_attn_version(void) { return "flashattn_b200 0.3 (sm_100a tcgen05/TMA forward)"; }
 
 }  // extern "C"
 
-// Watchdog record of the current device: {aborted, barrier tag, block, thread} (see sm100_ptx.cuh).
-// Synchronises the device.  Returns FA_OK or a cudaError_t.
-extern "C" int flash_attn_debug_status(unsigned int* out4) {
+// Watchdog record of the current device, {aborted, barrier tag, block, thread} (see sm100_ptx.cuh): a pending one
+// (aborted = 1: the next call will return FA_ERR_WATCHDOG) or else the last one that was reported (aborted = 0 and
+// the fields of that report; all zero if there never was one).  Does not synchronise, does not clear.
+extern "C" int flash_attn_status(unsigned int* out4) {
     if (!out4) return FA_ERR_NULL_PTR;
+    int err = 0;
+    DeviceState* st = device_state(&err);
+    if (!st) return err;
+    const volatile unsigned int* h = st->wd_host;
+    if (h && h[0]) {
+        for (int i = 0; i < 4; i++) out4[i] = h[i];
+    } else {
+        out4[0] = 0;
+        for (int i = 1; i < 4; i++) out4[i] = st->wd_last[i];
+    }
+    return FA_OK;
+}
+// Test hooks: the same after a device synchronise / a one-thread kernel that raises the record the way a timed-out wait does.
+extern "C" int flash_attn_debug_status(unsigned int* out4) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return (int)e;
-    return (int)cudaMemcpyFromSymbol(out4, sm100::g_watchdog, 4 * sizeof(unsigned int));
+    return flash_attn_status(out4);
+}
+__global__ void fa_debug_trip_kernel(unsigned int tag) { sm100::watchdog_raise((int)tag); }
+extern "C" int flash_attn_debug_trip_watchdog(unsigned int tag, void* stream) {
+    int err = 0;
+    if (!device_state(&err)) return err;
+    fa_debug_trip_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(tag);
+    return (int)cudaGetLastError();
 }
 
 #ifdef FA_TIMING
@@ -603,11 +637,6 @@ extern "C" int flash_attn_debug_timing(unsigned long long* out32, int reset) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return (int)e;
     unsigned long long z[64] = {0};
-    if (use_pair_kernel()) {   // 64 counters
-        e = cudaMemcpyFromSymbol(out32, fa_pair::g_timing_pair, 64 * sizeof(unsigned long long));
-        if (e == cudaSuccess && reset) e = cudaMemcpyToSymbol(fa_pair::g_timing_pair, z, 64 * sizeof(unsigned long long));
-        return (int)e;
-    }
     e = cudaMemcpyFromSymbol(out32, fa::g_timing, 32 * sizeof(unsigned long long));
     if (e == cudaSuccess && reset) e = cudaMemcpyToSymbol(fa::g_timing, z, 32 * sizeof(unsigned long long));
     return (int)e;
@@ -620,14 +649,6 @@ extern "C" int flash_attn_debug_work_item(int w, int B, int H, int Nq, int Nkv, 
                                           int* total, int* bh, int* q0, int* n0, int* n1) {
     if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
     fa::Params p = make_params(B * H, Nq, Nkv, D, causal, shift);
-    if (use_pair_kernel()) {
-        const fa_pair::Params pp = make_pair_params(p, D);
-        *total = pp.total_work;
-        if (w < 0 || w >= pp.total_work) return FA_ERR_BAD_SHAPE;
-        fa_pair::WorkItem it = fa_pair::decode_work(w, pp);
-        *bh = it.bh; *q0 = it.q0; *n0 = it.n0; *n1 = it.n1;
-        return FA_OK;
-    }
     *total = p.total_work;
     if (w < 0 || w >= p.total_work) return FA_ERR_BAD_SHAPE;
     fa::WorkItem it = fa::decode_work(w, p);
@@ -638,7 +659,6 @@ extern "C" int flash_attn_debug_work_item(int w, int B, int H, int Nq, int Nkv, 
 // kernel the CTAs per unit (1 or 2), each holding one tile
 extern "C" int flash_attn_debug_tiles_per_item(int D) {
     if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
-    if (use_pair_kernel()) return pair_cta_group_for(D);
 #ifdef FA_SINGLE_TILE_MODE
     return make_params(1, 1, 1, D, 0, 0).single ? 1 : 2;
 #else

@@ -64,29 +64,49 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Blocking wait with a watchdog.  A protocol bug must not hang the GPU: after ~2^31 cycles (>1 s;
-// no legitimate wait here exceeds a few ms) the waiter records who it was in g_watchdog and raises
-// a device-wide abort flag; every wait that is in its slow path then returns at once, so the
-// kernel drains and exits with garbage results instead of spinning.  The host reads the record
-// through flash_attn_debug_status().  No function call / printf here on purpose: a call in the
-// kernel makes ptxas ignore the per-role setmaxnreg budgets and spill the softmax warps.
-__device__ unsigned int g_watchdog[4];   // {abort flag, barrier tag, block, thread}
+// Blocking wait with a watchdog.  A protocol bug must not hang the GPU: after kWatchdogNs of wall time (no
+// legitimate wait here exceeds a few ms; the margin covers time-slicing and debuggers) the waiter records who it
+// was, raises a device-wide abort flag that releases every other wait in its slow path, and the kernel drains and
+// exits with garbage results instead of spinning.  The record is mirrored into zero-copy host memory
+// (g_watchdog_host, installed by the launcher), where the launcher finds it at the start of its next call without
+// synchronising, reports it once as FA_ERR_WATCHDOG and clears both copies (fa_api.cu: take_watchdog).  No function
+// call / printf / trap here on purpose: a call in the kernel makes ptxas ignore the per-role setmaxnreg budgets and
+// spill the softmax warps.
+__device__ unsigned int g_watchdog[4];         // {abort flag, barrier tag, block, thread}
+__device__ unsigned int* g_watchdog_host;      // device alias of the launcher's pinned mirror, or null
+constexpr unsigned long long kWatchdogNs = 10ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ bool watchdog_aborted() {
     return *reinterpret_cast<volatile unsigned int*>(&g_watchdog[0]) != 0u;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void watchdog_raise(int tag) {
+    if (atomicExch(&g_watchdog[0], 1u) == 0u) {
+        g_watchdog[1] = (unsigned)tag;
+        g_watchdog[2] = blockIdx.x;
+        g_watchdog[3] = threadIdx.x;
+        volatile unsigned int* h = g_watchdog_host;
+        if (h) {
+            h[1] = (unsigned)tag;
+            h[2] = blockIdx.x;
+            h[3] = threadIdx.x;
+            __threadfence_system();
+            h[0] = 1u;
+        }
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_timer_ns();
     uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
         if ((++polls & 63u) == 0u) {
             if (watchdog_aborted()) return;
-            if (clock64() - t0 > (1ll << 31)) {
-                if (atomicExch(&g_watchdog[0], 1u) == 0u) {
-                    g_watchdog[1] = (unsigned)tag;
-                    g_watchdog[2] = blockIdx.x;
-                    g_watchdog[3] = threadIdx.x;
-                }
+            if (global_timer_ns() - t0 > kWatchdogNs) {
+                watchdog_raise(tag);
                 return;
             }
         }
@@ -139,17 +159,13 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
 // mbar_wait for barriers that also receive arrivals from the peer CTA (acquire at cluster scope)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag) {
     if (mbar_try_wait_cluster(bar, parity)) return;
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_timer_ns();
     uint32_t polls = 0;
     while (!mbar_try_wait_cluster(bar, parity)) {
         if ((++polls & 63u) == 0u) {
             if (watchdog_aborted()) return;
-            if (clock64() - t0 > (1ll << 31)) {
-                if (atomicExch(&g_watchdog[0], 1u) == 0u) {
-                    g_watchdog[1] = (unsigned)tag;
-                    g_watchdog[2] = blockIdx.x;
-                    g_watchdog[3] = threadIdx.x;
-                }
+            if (global_timer_ns() - t0 > kWatchdogNs) {
+                watchdog_raise(tag);
                 return;
             }
         }

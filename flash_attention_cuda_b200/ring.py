@@ -203,6 +203,25 @@ def release_peer_kv() -> None:
     _peer_kv.clear()
 
 
+def _check_chunks(q, k, v):
+    """The CUDA partial / merge path is FP16 only and reads plain contiguous [B, H, C, D] chunks (a slice of a
+    [B, H, N, D] tensor along N is not one): refuse anything else instead of reading it with the wrong strides or format."""
+    import torch
+    if len(q) != 2 or len(k) != 2 or len(v) != 2:
+        raise ValueError("q, k, v must each be a pair (low chunk, high chunk)")
+    ref = q[0]
+    for name, pair in (("q", q), ("k", k), ("v", v)):
+        for t in pair:
+            if t.shape != ref.shape or t.dim() != 4:
+                raise ValueError(f"{name}: every chunk must be [B, H, C, D] of one shape")
+            if not t.is_contiguous():
+                raise ValueError(f"{name}: chunks must be contiguous [B, H, C, D] tensors")
+            if t.device != ref.device or t.dtype != ref.dtype:
+                raise ValueError(f"{name}: all chunks must share one device and dtype")
+    if ref.is_cuda and ref.dtype != torch.float16:
+        raise TypeError("context parallelism runs the FP16 partial/merge path; got " + str(ref.dtype))
+
+
 def _partial_workspace(q, world, causal, schedule):
     """Partial states (one per chunk pair, write-only), cached per (device, shape): a step allocates nothing
     and zero-fills nothing."""
@@ -239,6 +258,7 @@ def pull_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
     """Context-parallel forward with peer pulls (module docstring).  Same arguments and result as
     `ring_attention_forward`.  `peer` is a PeerKV (default: the cached one for this shape); tests inject an
     object with the same begin / prefetch / wait / done / end methods together with rank and world."""
+    _check_chunks(q, k, v)
     partial = partial or _cuda_partial
     finalize = finalize or _cuda_finalize
     if rank is None or world is None:
@@ -283,6 +303,7 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
     import torch
     import torch.distributed as dist
 
+    _check_chunks(q, k, v)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if exchange is None:
@@ -319,33 +340,36 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
         old_margin = set_sm_margin(int(os.environ.get("FLASH_ATTN_RING_SM_MARGIN", DEFAULT_RING_SM_MARGIN)))
 
     qa = zigzag_chunks(rank, world)
-    for hop in range(world):
-        src = (rank - hop) % world
-        reqs = []
-        if hop + 1 < world:
-            ops = []
-            for t_send, t_recv in zip(cur, nxt):
-                ops.append(dist.P2POp(dist.isend, t_send, send_to, group))
-                ops.append(dist.P2POp(dist.irecv, t_recv, recv_from, group))
-            if on_cuda:
-                comm_stream.wait_stream(torch.cuda.current_stream(dev))   # cur is ready to be read
-                with torch.cuda.stream(comm_stream):
+    try:
+        for hop in range(world):
+            src = (rank - hop) % world
+            reqs = []
+            if hop + 1 < world:
+                ops = []
+                for t_send, t_recv in zip(cur, nxt):
+                    ops.append(dist.P2POp(dist.isend, t_send, send_to, group))
+                    ops.append(dist.P2POp(dist.irecv, t_recv, recv_from, group))
+                if on_cuda:
+                    comm_stream.wait_stream(torch.cuda.current_stream(dev))   # cur is ready to be read
+                    with torch.cuda.stream(comm_stream):
+                        reqs = dist.batch_isend_irecv(ops)
+                else:
                     reqs = dist.batch_isend_irecv(ops)
-            else:
-                reqs = dist.batch_isend_irecv(ops)
-        kb = zigzag_chunks(src, world)
-        for qi, ki, diag in schedule[hop]:
-            partial(q[qi], cur[ki], cur[2 + ki], o_part[qi][used[qi]], ml[qi][used[qi]], bool(diag),
-                    qa[qi] * C, kb[ki] * C, False)
-            used[qi] += 1
-        if hop + 1 < world:
-            for r in reqs:
-                r.wait()
-            if on_cuda:
-                torch.cuda.current_stream(dev).wait_stream(comm_stream)
-                comm_stream.wait_stream(torch.cuda.current_stream(dev))   # kernels that read cur are ordered first
-            cur, nxt = nxt, ws["recv"][(hop + 1) & 1]
-    if old_margin is not None:
-        from . import set_sm_margin
-        set_sm_margin(old_margin)
+            kb = zigzag_chunks(src, world)
+            for qi, ki, diag in schedule[hop]:
+                partial(q[qi], cur[ki], cur[2 + ki], o_part[qi][used[qi]], ml[qi][used[qi]], bool(diag),
+                        qa[qi] * C, kb[ki] * C, False)
+                used[qi] += 1
+            if hop + 1 < world:
+                for r in reqs:
+                    r.wait()
+                if on_cuda:
+                    torch.cuda.current_stream(dev).wait_stream(comm_stream)
+                    comm_stream.wait_stream(torch.cuda.current_stream(dev))   # kernels that read cur are ordered first
+                cur, nxt = nxt, ws["recv"][(hop + 1) & 1]
+    finally:
+        # the margin is process-global: an exception in a hop must not leave every later launch on fewer SMs
+        if old_margin is not None:
+            from . import set_sm_margin
+            set_sm_margin(old_margin)
     return _merge_partials(q, o_part, ml, used, finalize)

@@ -35,7 +35,8 @@ extern "C" {
 #define FA_ERR_BAD_SHAPE (-4)  /* B, H or N < 1, or B*H / N beyond the tensor-map limits */
 #define FA_ERR_UNSUPPORTED_ARCH (-5) /* current device is not compute capability 10.x */
 #define FA_ERR_TENSORMAP (-6)        /* cuTensorMapEncodeTiled failed */
-#define FA_ERR_WORKSPACE (-7)        /* workspace too small / missing for an _ex call */
+#define FA_ERR_WORKSPACE (-7)        /* workspace too small / missing for an _ex call; more than 1024 launches recorded into CUDA graphs */
+#define FA_ERR_WATCHDOG (-8)         /* an EARLIER kernel of this process timed out on an internal barrier (see flash_attn_status) */
 
 /* Replaces flash_attention_v9_dispatch (FA.cu:606-663).  Argument order is the one the
  * north-star names: q, k, v, o, B, H, N, D, causal, stream. */
@@ -113,10 +114,21 @@ int flash_attn_peer_close(void* ptr);
 int flash_attn_peer_free(void* ptr);
 int flash_attn_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 
+/* Kernel watchdog.  Every barrier wait inside the kernel gives up after 10 s (a protocol bug, or a device so
+ * oversubscribed that a CTA did not run for that long): the kernel then drains, its output is garbage, and a record
+ * {aborted, barrier tag, block, thread} is left for the host.  The launcher reads it without synchronising at the
+ * start of every flash_attn_fwd / _bf16 / _ex call (and at the end of flash_attn_fwd_host): the first call after the
+ * abort returns FA_ERR_WATCHDOG instead of launching, clears the record and re-arms the device, so later calls work.
+ * flash_attn_status() shows the pending record (out4[0] = 1) or the last reported one (out4[0] = 0) of the current
+ * device; it neither synchronises nor clears.  (The reference has no such path: its kernel cannot hang, and a CUDA
+ * error ends the process, FA.cu:22-30.) */
+int flash_attn_status(unsigned int* out4);
+
 /* Number of kernels this library has launched in the calling process (all threads). */
 unsigned long long flash_attn_launch_count(void);
 
-/* Frees the per-device caches (staging buffers of flash_attn_fwd_host). */
+/* Frees the per-device state (scheduler words, watchdog mirror, descriptor cache, staging buffers and streams of
+ * flash_attn_fwd_host) after synchronising each device; the next call sets a device up again. */
 void flash_attn_destroy(void);
 
 const char* flash_attn_error_string(int code);

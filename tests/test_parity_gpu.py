@@ -334,21 +334,6 @@ def test_config5_full_size_row_sampled(fa):
     _sampled_check(fa, 1, 32, 131072, 128, 1, heads=[0, 31], seed=5)
 
 
-# ---- the experimental CTA-pair kernel (FLASH_ATTN_B200_KERNEL=pair, csrc/fa_fwd_pair_sm100.cuh) ----
-# The kernel choice is read once per process, so the same parity tests run again in a child process.
-@pytest.mark.skipif(os.environ.get("FLASH_ATTN_B200_KERNEL") == "pair", reason="this process already runs the pair kernel")
-def test_experimental_pair_kernel_passes_the_same_parity_tests(fa):
-    import subprocess
-    import sys
-    env = dict(os.environ, FLASH_ATTN_B200_KERNEL="pair")
-    keep = ("reference_harness or causal_long or ragged or head_dim_64 or batch_greater or rescale or row0 or v_ones "
-            "or linearity or golden or partial_state or splitk_merge or canaries or many_heads or full_size_row_sampled")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k", keep],
-                       env=env, capture_output=True, text=True, timeout=1500)
-    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
-    assert "passed" in r.stdout
-
-
 # ---- peer-readable blocks (flash_attn_peer_*): another process maps this process's block and pulls it ----
 _PEER_CHILD = r'''
 import sys, torch
