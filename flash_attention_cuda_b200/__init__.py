@@ -132,6 +132,13 @@ def lib() -> ctypes.CDLL:
     L.flash_attn_version.restype = ctypes.c_char_p
     L.flash_attn_debug_work_item.argtypes = [ci, ci, ci, ci, ci, ci, ci, ll] + [ctypes.POINTER(ci)] * 5
     L.flash_attn_debug_work_item.restype = ci
+    if hasattr(L, "flash_attn_debug_work_item_split"):   # absent from archived A/B builds of older kernels
+        L.flash_attn_debug_work_item_split.argtypes = [ci, ci, ci, ci, ci, ci, ci, ll] + [ctypes.POINTER(ci)] * 5
+        L.flash_attn_debug_work_item_split.restype = ci
+        L.flash_attn_debug_set_split.argtypes = [ci]
+        L.flash_attn_debug_set_split.restype = None
+        L.flash_attn_debug_uses_split.argtypes = [ci, ci, ci, ci]
+        L.flash_attn_debug_uses_split.restype = ci
     if hasattr(L, "flash_attn_debug_tiles_per_item"):   # absent from archived A/B builds of older kernels
         L.flash_attn_debug_tiles_per_item.argtypes = [ci]
         L.flash_attn_debug_tiles_per_item.restype = ci
@@ -336,16 +343,26 @@ def launch_count() -> int:
     return int(lib().flash_attn_launch_count())
 
 
-def work_item(w: int, B: int, H: int, Nq: int, Nkv: int, D: int, causal: bool, shift: int = 0):
-    """Host mirror of the device work decomposition (scheduler tests)."""
+def work_item(w: int, B: int, H: int, Nq: int, Nkv: int, D: int, causal: bool, shift: int = 0, split: bool = False):
+    """Host mirror of the device work decomposition (scheduler tests).  split: the short-sequence mode in which an item
+    is one Q tile and n0 / n1 are its even / odd KV tiles (fa_fwd_sm100.cuh)."""
     vals = [ctypes.c_int() for _ in range(5)]
-    rc = lib().flash_attn_debug_work_item(w, B, H, Nq, Nkv, D, 1 if causal else 0, shift,
-                                          *[ctypes.byref(x) for x in vals])
+    fn = lib().flash_attn_debug_work_item_split if split else lib().flash_attn_debug_work_item
+    rc = fn(w, B, H, Nq, Nkv, D, 1 if causal else 0, shift, *[ctypes.byref(x) for x in vals])
     check(rc)
     total, bh, q0, n0, n1 = (x.value for x in vals)
-    return {"total": total, "bh": bh, "q0": q0, "n0": n0, "n1": n1, "n": max(n0, n1)}
+    return {"total": total, "bh": bh, "q0": q0, "n0": n0, "n1": n1, "n": n0 + n1 if split else max(n0, n1)}
+
+
+def set_split(mode) -> None:
+    """Work decomposition of flash_attn_fwd from now on: None = automatic, False = pair items, True = split mode."""
+    lib().flash_attn_debug_set_split(-1 if mode is None else (1 if mode else 0))
+
+
+def uses_split(B: int, H: int, N: int, causal: bool) -> bool:
+    return bool(lib().flash_attn_debug_uses_split(B, H, N, 1 if causal else 0))
 
 
 def tiles_per_item(D: int) -> int:
-    """128-row Q tiles one work item covers (2; 1 in single-tile mode)."""
+    """128-row Q tiles one pair-mode work item covers."""
     return int(lib().flash_attn_debug_tiles_per_item(D))

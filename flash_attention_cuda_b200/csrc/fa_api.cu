@@ -27,7 +27,7 @@ constexpr int kGroupMB = 32;       // K+V bytes of one scheduling group of heads
 #define FA_POLY_LONG 1
 #endif
 #ifndef FA_POLY_D64
-#define FA_POLY_D64 0
+#define FA_POLY_D64 1
 #endif
 constexpr int kPolyLong = FA_POLY_LONG, kPolyD64 = FA_POLY_D64;
 
@@ -181,7 +181,27 @@ int validate(const void* q, const void* k, const void* v, const void* o, int B, 
     return FA_OK;
 }
 
-fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shift) {
+// Split mode (fa_fwd_sm100.cuh): one Q tile per work item, its KV tiles alternating between the CTA's two tile slots.
+// Used where pair items are too few to keep the machine busy (use_split below).
+// FLASH_ATTN_B200_SPLIT = 0 / 1 forces it off / on (A/B runs); flash_attn_debug_set_split overrides at run time.
+std::atomic<int> g_split_override{-2};     // -2: read the environment; -1: automatic; 0 / 1: forced
+bool use_split(int BH, int Nq, int causal, int num_sms) {
+    int o = g_split_override.load(std::memory_order_relaxed);
+    if (o == -2) {
+        const char* e = getenv("FLASH_ATTN_B200_SPLIT");
+        o = e && (e[0] == '0' || e[0] == '1') ? e[0] - '0' : -1;
+        g_split_override.store(o, std::memory_order_relaxed);
+    }
+    if (o >= 0) return o == 1;
+    // measured on B200 (profiles/r02_c4_split_ab.log, H = 32, D = 128): with at most one single-tile item per SM split mode
+    // wins by 8-14 % (N = 512); up to two per SM it still wins under a causal mask (N = 768: +9 %, N = 1024: +5 % hot /
+    // +13 % cold L2), where item lengths differ, and loses 10 % without one; beyond that pair items win (a K/V tile then
+    // serves two Q tiles and the machine is full either way)
+    const long long items = (long long)BH * ((Nq + fa::kBlockM - 1) / fa::kBlockM);
+    return items <= num_sms || (causal && items <= 2LL * num_sms);
+}
+
+fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shift, bool split = false) {
     fa::Params p;
     memset(&p, 0, sizeof p);
     p.Nq = Nq; p.Nkv = Nkv; p.BH = BH;
@@ -189,20 +209,8 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     if (shift > 0x3fffffffLL) shift = 0x3fffffffLL;
     if (shift < -0x3fffffffLL) shift = -0x3fffffffLL;
     p.shift = (int)shift;
-    // experimental: one Q tile per work item (shorter dependency chains for grids that cannot fill the machine);
-    // only in -DFA_SINGLE_TILE_MODE builds and with FLASH_ATTN_B200_ITEM_TILES=1 -- not yet measured on a GPU
-#ifdef FA_SINGLE_TILE_MODE
-    static const int single = [] {
-        const char* e = getenv("FLASH_ATTN_B200_ITEM_TILES");
-        return e && atoi(e) == 1 ? 1 : 0;
-    }();
-#else
-    const int single = 0;
-#endif
-#ifdef FA_SINGLE_TILE_MODE
-    p.single = single;
-#endif
-    p.nqp = single ? (Nq + fa::kBlockM - 1) / fa::kBlockM : (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
+    p.split = split ? 1 : 0;
+    p.nqp = split ? (Nq + fa::kBlockM - 1) / fa::kBlockM : (Nq + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM);
     const long long tw = (long long)BH * p.nqp;
     p.total_work = (int)tw;
     // heads per scheduling group: K+V of the group <= kGroupMB (B200's 126 MB L2 is two 63 MB halves, and a line
@@ -324,7 +332,9 @@ int flash_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, 
                    void* stream) {
     int rc = validate(q, k, v, o, B, H, N, N, D);
     if (rc != FA_OK) return rc;
-    fa::Params p = make_params(B * H, N, N, D, causal, 0);
+    DeviceState* st = device_state(&rc);
+    if (!st) return rc;
+    fa::Params p = make_params(B * H, N, N, D, causal, 0, use_split(B * H, N, causal, st->num_sms));
     p.o = static_cast<__half*>(o);
     return run(q, k, v, p, D, static_cast<cudaStream_t>(stream));
 }
@@ -333,7 +343,9 @@ int flash_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, in
                         void* stream) {
     int rc = validate(q, k, v, o, B, H, N, N, D);
     if (rc != FA_OK) return rc;
-    fa::Params p = make_params(B * H, N, N, D, causal, 0);
+    DeviceState* st = device_state(&rc);
+    if (!st) return rc;
+    fa::Params p = make_params(B * H, N, N, D, causal, 0, use_split(B * H, N, causal, st->num_sms));
     p.o = static_cast<__half*>(o);       // 16-bit elements either way; the kernel instantiation decides the format
     return run(q, k, v, p, D, static_cast<cudaStream_t>(stream), /*bf16=*/true);
 }
@@ -398,7 +410,11 @@ static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const 
         const int v = env ? atoi(env) : 0;
         return v >= 1 && v <= kHostChunks ? v : kHostChunksDefault;
     }();
-    const int chunks = BH < want_chunks ? BH : want_chunks;
+    // a chunk should carry enough bytes to amortise its three copies, two events and one launch: >= 16 MiB of input
+    int chunks = (int)((3 * bytes) >> 24);
+    if (chunks > want_chunks) chunks = want_chunks;
+    if (chunks > BH) chunks = BH;
+    if (chunks < 1) chunks = 1;
     const size_t head_bytes = (size_t)N * D * sizeof(__half);
     int h0 = 0;
     for (int c = 0; c < chunks; c++) {
@@ -480,7 +496,7 @@ int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_att
     DeviceState* st = device_state(&err);
     if (!st) return err;
     if ((long long)B * H > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
-    fa::Params p = make_params(B * H, N, N, D, causal, 0);
+    fa::Params p = make_params(B * H, N, N, D, causal, 0, use_split(B * H, N, causal, st->num_sms));
     if ((long long)p.BH * p.nqp > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
     info->cta_group = 1;
     info->regs_per_thread = attr.numRegs;
@@ -644,24 +660,38 @@ extern "C" int flash_attn_debug_timing(unsigned long long* out32, int reset) {
 #endif
 
 // Host-side mirror of the device work decomposition, exported for the scheduler tests
-// (every (bh, q-tile) exactly once, heavy-first, masked tiles skipped).
+// (every (bh, q-tile) exactly once, heavy-first, masked tiles skipped).  split: 0 = pair items, 1 = split mode.
 extern "C" int flash_attn_debug_work_item(int w, int B, int H, int Nq, int Nkv, int D, int causal, long long shift,
                                           int* total, int* bh, int* q0, int* n0, int* n1) {
     if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
-    fa::Params p = make_params(B * H, Nq, Nkv, D, causal, shift);
+    fa::Params p = make_params(B * H, Nq, Nkv, D, causal, shift, false);
     *total = p.total_work;
     if (w < 0 || w >= p.total_work) return FA_ERR_BAD_SHAPE;
     fa::WorkItem it = fa::decode_work(w, p);
     *bh = it.bh; *q0 = it.q0; *n0 = it.n0; *n1 = it.n1;
     return FA_OK;
 }
-// 128-row Q tiles a work item covers: 2 for the default kernel (one CTA, two tiles); for the pair
-// kernel the CTAs per unit (1 or 2), each holding one tile
+extern "C" int flash_attn_debug_work_item_split(int w, int B, int H, int Nq, int Nkv, int D, int causal, long long shift,
+                                                int* total, int* bh, int* q0, int* n0, int* n1) {
+    if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+    fa::Params p = make_params(B * H, Nq, Nkv, D, causal, shift, true);
+    *total = p.total_work;
+    if (w < 0 || w >= p.total_work) return FA_ERR_BAD_SHAPE;
+    fa::WorkItem it = fa::decode_work(w, p);
+    *bh = it.bh; *q0 = it.q0; *n0 = it.n0; *n1 = it.n1;
+    return FA_OK;
+}
+// 128-row Q tiles a pair-mode work item covers
 extern "C" int flash_attn_debug_tiles_per_item(int D) {
     if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
-#ifdef FA_SINGLE_TILE_MODE
-    return make_params(1, 1, 1, D, 0, 0).single ? 1 : 2;
-#else
     return 2;
-#endif
+}
+// -1 automatic (use_split), 0 never, 1 always: which work decomposition flash_attn_fwd uses from now on (A/B runs, tests)
+extern "C" void flash_attn_debug_set_split(int mode) { g_split_override.store(mode < -1 || mode > 1 ? -1 : mode, std::memory_order_relaxed); }
+// 1 when flash_attn_fwd would run this shape in split mode on the current device
+extern "C" int flash_attn_debug_uses_split(int B, int H, int N, int causal) {
+    int err = 0;
+    DeviceState* st = device_state(&err);
+    if (!st) return err;
+    return use_split(B * H, N, causal, st->num_sms) ? 1 : 0;
 }

@@ -45,7 +45,6 @@
 //   -DFA_STREAM        streamed softmax (softmax_tile_stream: S read in chunks, exponentials against the row's current
 //                      reference, lazy rescale at the end of the tile): parity-clean, 1 % slower (r02_stream_experiment.txt)
 //   -DFA_STREAM_S      second half of S re-read from TMEM instead of held in registers (r01_softmax_schedule.txt)
-//   -DFA_SINGLE_TILE_MODE  one Q tile per work item, selected at run time by FLASH_ATTN_B200_ITEM_TILES=1 (not yet run)
 //   -DFA_P_PARTS=3     P in three pieces;  -DFA_REGS_SOFTMAX / -DFA_REGS_OTHER  setmaxnreg budgets
 //                      (r01_v4b_defer_group_ab.log)
 #pragma once
@@ -115,7 +114,8 @@ struct Cfg {
     static constexpr int kSmemKV = kStages * kTileBytes;
     static constexpr int kBarOffset = kSmemQ + kSmemKV;
     static constexpr int kNumBars = 4 + 2 * kStages + 14 + 4 + 4;
-    static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 32 + 1024;  // +32: tmem slot, scheduler slots; +1024: manual alignment slack
+    static constexpr int kMlOffset = kBarOffset + kNumBars * 8 + 32;           // +32: tmem slot, scheduler slots
+    static constexpr int kSmemBytes = kMlOffset + kBlockM * 8 + 1024;          // (m, l) of tile slot 1 (split mode); +1024: manual alignment slack
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
     static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
     static constexpr uint32_t kIdescQK = umma_idesc_f16(kBlockM, kBlockN, 0, 0);
@@ -131,10 +131,8 @@ struct Params {
     int Nq, Nkv, BH;
     int causal;
     int shift;          // q_offset - kv_offset: key c visible to query r iff c <= r + shift
-    int nqp;            // work items per head: Q tile pairs, ceil(Nq / 256) (single: Q tiles, ceil(Nq / 128))
-#ifdef FA_SINGLE_TILE_MODE
-    int single;         // 1: a work item is ONE Q tile (experimental, FLASH_ATTN_B200_ITEM_TILES=1; tile 1 of every item absent)
-#endif
+    int nqp;            // work items per head: Q tile pairs, ceil(Nq / 256) (split mode: Q tiles, ceil(Nq / 128))
+    int split;          // 1: a work item is ONE Q tile and its KV tiles alternate between the CTA's two tile slots (below)
     int total_work;     // BH * nqp
     int group_heads;    // heads per scheduling group (their K/V working set is sized to stay in L2)
     int partial_mode;
@@ -145,19 +143,19 @@ struct Params {
     float scale_log2;   // scale * log2(e)
 };
 
-// Single-tile work items are compiled in only with -DFA_SINGLE_TILE_MODE (and then selected at run time by
-// FLASH_ATTN_B200_ITEM_TILES=1): the product build keeps exactly the code that was measured.
-#ifdef FA_SINGLE_TILE_MODE
-#define FA_SINGLE(p) ((p).single)
-#else
-#define FA_SINGLE(p) 0
-#endif
-
+// Split mode (short sequences, fa_api.cu: use_split).  With few and short work items the kernel is bound by the length of one
+// item's chain of KV steps, not by throughput (BASELINE config 1: 128 pair items for 148 SMs, up to 8 steps of ~1.4 us).
+// The reference's answer to that is a split-K grid axis with a separate merge kernel (FA.cu:170-176, 460-496, 559-598;
+// never dispatched).  Here the split stays inside the CTA: a work item is ONE 128-row Q tile, the two tile slots
+// (S0/O0 + softmax warps 0-3, S1/O1 + softmax warps 4-7) take its even / odd KV tiles, and the two partial states are merged
+// with the algebra of FA.cu:575-597 through shared memory in the epilogue.  Twice the items, half the chain, the tensor pipe
+// still fed by two independent chains; the price is that a K/V tile now serves one Q tile instead of two.
 // ---- work decomposition (shared by host tests and every warp role) ----
 struct WorkItem {
-    int bh, q0;      // head index, first local query row of the pair
-    int n0, n1;      // KV tiles the two Q tiles need (0 = nothing visible / tile absent)
-    int tile1;       // the item has a second Q tile (rows q0+128..): false past the end of Q and in single-tile mode
+    int bh, q0;      // head index, first local query row of the item
+    int n0, n1;      // KV tiles the two tile slots process (pair mode: per Q tile; split mode: even / odd tiles of the one Q tile)
+    int nkv;         // KV tiles the producer loads for the item
+    int tile1;       // the item has a second Q tile (rows q0+128..): false past the end of Q and in split mode
 };
 __host__ __device__ inline int kv_trip_count(int q_start, int Nq, int Nkv, int causal, int shift) {
     if (q_start >= Nq) return 0;
@@ -171,8 +169,8 @@ __host__ __device__ inline int kv_trip_count(int q_start, int Nq, int Nkv, int c
     return (int)((vis + kBlockN - 1) / kBlockN);
 }
 // Work order (replaces GRID_SWAP / reversed q-blocks, FA.cu:103-112).  Heads are taken in groups whose
-// K/V fit comfortably in L2; inside a group the order is heaviest Q pair first ACROSS the group's
-// heads (causal: the last pair sees the most keys), so the dynamic scheduler hands out long items
+// K/V fit comfortably in L2; inside a group the order is heaviest item first ACROSS the group's
+// heads (causal: the last Q tiles see the most keys), so the dynamic scheduler hands out long items
 // early and the tail of the launch is made of the lightest ones, while the CTAs running at any moment
 // still share a few heads' K/V through L2.
 __host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
@@ -184,10 +182,19 @@ __host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
     if (heads > p.group_heads) heads = p.group_heads;
     const int qp = p.nqp - 1 - r / heads;
     it.bh = g * p.group_heads + r % heads;
-    it.q0 = qp * (FA_SINGLE(p) ? 1 : 2) * kBlockM;
-    it.tile1 = !FA_SINGLE(p) && it.q0 + kBlockM < p.Nq;
+    if (p.split) {
+        it.q0 = qp * kBlockM;
+        it.tile1 = 0;
+        it.nkv = kv_trip_count(it.q0, p.Nq, p.Nkv, p.causal, p.shift);
+        it.n0 = (it.nkv + 1) / 2;      // KV tiles 0, 2, 4, ...
+        it.n1 = it.nkv / 2;            // KV tiles 1, 3, 5, ...
+        return it;
+    }
+    it.q0 = qp * 2 * kBlockM;
+    it.tile1 = it.q0 + kBlockM < p.Nq;
     it.n0 = kv_trip_count(it.q0, p.Nq, p.Nkv, p.causal, p.shift);
     it.n1 = it.tile1 ? kv_trip_count(it.q0 + kBlockM, p.Nq, p.Nkv, p.causal, p.shift) : 0;
+    it.nkv = it.n0 > it.n1 ? it.n0 : it.n1;
     return it;
 }
 
@@ -734,6 +741,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #ifdef FA_TIMING
     long long k_c0 = 0;
     unsigned long long k_t0 = 0;
+    const long long k_c0_all = clock64();
     if (threadIdx.x == 0) {
         k_c0 = clock64();
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_t0));
@@ -824,7 +832,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             __syncwarp();
             if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
-            const int nmax = wi.n0 > wi.n1 ? wi.n0 : wi.n1;
+            const int nmax = wi.nkv;
             const bool have_q1 = wi.tile1 != 0;
             // slot it&1 is free once the item two back has issued its last QK^T and stored its O tiles
             mbar_wait(bar_q_empty + 8 * slot, ((it >> 1) & 1u) ^ 1u, 1);
@@ -836,22 +844,32 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                                     bar_q_full + 8 * slot, pn * 64, wi.q0 + t * kBlockM, wi.bh);
             }
             __syncwarp();
-            for (int j = 0; j < nmax; j++) {
+            auto load_kv = [&](const CUtensorMap* tm, int j) {
+                const uint32_t full = bar_kv_full + 8 * ring.idx;
+                mbar_wait(bar_kv_empty + 8 * ring.idx, ring.phase ^ 1u, 2);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(full, C::kTileBytes);
+                    const uint32_t dst = sKV + ring.idx * C::kTileBytes;
+#pragma unroll
+                    for (int pn = 0; pn < C::kPanels; pn++)
+                        tma_load_3d(dst + pn * C::kPanelBytes, tm, full, pn * 64, j * kBlockN, wi.bh);
+                }
+                __syncwarp();
+                ring.advance<C::kStages>();
+            };
+            if (!p.split) {
                 // ring order K_0 V_0 K_1 V_1 ... (the order the MMA warp releases them in)
-#pragma unroll
-                for (int kv = 0; kv < 2; kv++) {
-                    const uint32_t full = bar_kv_full + 8 * ring.idx;
-                    mbar_wait(bar_kv_empty + 8 * ring.idx, ring.phase ^ 1u, 2);
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx(full, C::kTileBytes);
-                        const uint32_t dst = sKV + ring.idx * C::kTileBytes;
-#pragma unroll
-                        for (int pn = 0; pn < C::kPanels; pn++)
-                            tma_load_3d(dst + pn * C::kPanelBytes, kv == 0 ? &tmK : &tmV, full, pn * 64,
-                                        j * kBlockN, wi.bh);
-                    }
-                    __syncwarp();
-                    ring.advance<C::kStages>();
+                for (int j = 0; j < nmax; j++) {
+                    load_kv(&tmK, j);
+                    load_kv(&tmV, j);
+                }
+            } else {
+                // split mode: K_0 K_1 V_0 K_2 V_1 K_3 V_2 ... -- both tile slots get their first S at once
+                if (nmax > 0) load_kv(&tmK, 0);
+                if (nmax > 1) load_kv(&tmK, 1);
+                for (int j = 0; j < nmax; j++) {
+                    load_kv(&tmV, j);
+                    if (j + 2 < nmax) load_kv(&tmK, j + 2);
                 }
             }
         }
@@ -924,6 +942,59 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             if (nm <= 1) commit(bar_q_empty + 8 * slot);
         };
 
+        if (p.split) {
+            // One Q tile per item; slot t = j & 1 takes KV tile j.  Ring entries are consumed in the producer's order
+            // K_0 K_1 V_0 K_2 V_1 K_3 ...; tensor-pipe order PV_t(j) QK_t(j+2), t alternating, as in pair mode.
+            Ring r{0u, 0u};
+            uint32_t pph[2] = {0u, 0u};
+            auto split_prologue = [&](uint32_t itn, const WorkItem& wn) {
+                const uint32_t slot = itn & 1u;
+                const uint64_t qd = umma_smem_desc(sQ + (slot * 2) * C::kTileBytes, 16, 1024);
+                mbar_wait(bar_q_full + 8 * slot, (itn >> 1) & 1u, 10);
+                tc_fence_after();
+                for (int t = 0; t < 2 && t < wn.nkv; t++) {
+                    mbar_wait(bar_kv_full + 8 * r.idx, r.phase, 11);
+                    tc_fence_after();
+                    issue_qk(t ? tS1 : tS0, qd, sKV + r.idx * C::kTileBytes, bar_s_full + 8 * t);
+                    commit(bar_kv_empty + 8 * r.idx);
+                    r.advance<C::kStages>();
+                }
+                if (wn.nkv <= 2) commit(bar_q_empty + 8 * slot);   // the last QK^T of the item has been issued
+            };
+            int w = next_work(0);
+            WorkItem wi;
+            if (w >= 0) {
+                wi = decode_work(w, p);
+                split_prologue(0u, wi);
+            }
+            for (; w >= 0; ++it) {
+                const uint32_t slot = it & 1u;
+                const uint64_t qd = umma_smem_desc(sQ + (slot * 2) * C::kTileBytes, 16, 1024);
+                const int n = wi.nkv;
+                for (int j = 0; j < n; j++) {
+                    const int t = j & 1;
+                    mbar_wait(bar_kv_full + 8 * r.idx, r.phase, 12);      // V_j
+                    issue_pv(t ? tO1 : tO0, t ? tS1 : tS0, sKV + r.idx * C::kTileBytes, j >= 2, bar_p_full + 32 * t,
+                             pph[t], bar_o_full + 8 * t, bar_o_half + 8 * t, 13 + t);
+                    pph[t] ^= 1u;
+                    commit(bar_kv_empty + 8 * r.idx);
+                    r.advance<C::kStages>();
+                    if (j + 2 < n) {
+                        mbar_wait(bar_kv_full + 8 * r.idx, r.phase, 15);  // K_{j+2}
+                        tc_fence_after();
+                        issue_qk(t ? tS1 : tS0, qd, sKV + r.idx * C::kTileBytes, bar_s_full + 8 * t);
+                        commit(bar_kv_empty + 8 * r.idx);
+                        r.advance<C::kStages>();
+                        if (j + 3 == n) commit(bar_q_empty + 8 * slot);   // that was the last reader of Q
+                    }
+                }
+                w = next_work(it + 1u);
+                if (w >= 0) {
+                    wi = decode_work(w, p);
+                    split_prologue(it + 1u, wi);
+                }
+            }
+        } else {
         int w = next_work(0);
         WorkItem wi;
         if (w >= 0) {
@@ -972,6 +1043,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 prologue(it + 1u, wi);
             }
         }
+        }   // pair mode
     } else if (warp == kStoreWarp) {
         // =============================== O tile store ===============================
         // The softmax warps stage O_t / l as fp16 in the item's (now idle) Q tile buffers, 128B-swizzled;
@@ -1024,8 +1096,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const int w = next_work(it);
             if (w < 0) break;
             const WorkItem wi = decode_work(w, p);
-            const int q_start = wi.q0 + t * kBlockM;
-            if (t == 1 && !wi.tile1) continue;                 // this Q tile does not exist (the store warp knows)
+            const int q_start = p.split ? wi.q0 : wi.q0 + t * kBlockM;   // split mode: both slots work on the one Q tile
+            if (t == 1 && !wi.tile1 && !p.split) continue;     // this Q tile does not exist (the store warp knows)
             const int n_t = t ? wi.n1 : wi.n0;
             const int row = q_start + row_in_tile;             // local query row
             // keys [0, lim) are visible to this row
@@ -1035,6 +1107,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const int lim = (int)lim_ll;
 
             float m_ref = -INFINITY, l_run = 0.f;
+#ifdef FA_TIMING
+            const long long ti0 = clock64();
+#endif
             for (int j = 0; j < n_t; j++) {
 #ifdef FA_TIMING
                 const long long tw0 = clock64();
@@ -1044,8 +1119,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 tc_fence_after();
 #ifdef FA_TIMING
                 const long long tw1 = clock64();
+                if (j == 0 && lane == 0 && (warp & 3) == 0) {     // item start -> first S of the item
+                    atomicAdd(&g_timing[8 + t * 2], (unsigned long long)(tw1 - ti0));
+                    atomicAdd(&g_timing[9 + t * 2], 1ull);
+                    if (it == 0) atomicAdd(&g_timing[12 + t], (unsigned long long)(tw1 - k_c0_all));   // kernel start -> first S
+                }
 #endif
-                const int k0 = j * kBlockN;
+                const int k0 = (p.split ? 2 * j + t : j) * kBlockN;        // split mode: slot t owns KV tiles t, t+2, ...
                 const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
 #if !defined(FA_STREAM) || defined(FA_SUM_GUARD)
                 if (need_mask)
@@ -1065,7 +1145,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #endif
                 ++pv_count;
 #ifdef FA_TIMING
+#ifdef FA_TIMING_ALL
+                if (lane == 0 && (warp & 3) == 0 && j > 0) {                   // short sequences: every tile but the first
+#else
                 if (lane == 0 && (warp & 3) == 0 && j > 0 && (j & 7) == 0) {   // sampled: 1 tile in 8
+#endif
                     const long long tw2 = clock64();
                     atomicAdd(&g_timing[t * 3 + 0], (unsigned long long)(tw1 - tw0));
                     atomicAdd(&g_timing[t * 3 + 1], (unsigned long long)(tw2 - tw1));
@@ -1075,6 +1159,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
 
             // ---- epilogue: O_t / l -> fp16 -> global (or the partial-state format) ----
+#ifdef FA_TIMING
+            const long long ti_ep = clock64();
+#endif
             if (n_t > 0) {
                 mbar_wait(my_o_full, (pv_count - 1u) & 1u, 30 + t);
                 tc_fence_after();
@@ -1087,7 +1174,78 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
             const bool row_ok = row < p.Nq;
             const size_t grow = (size_t)wi.bh * p.Nq + row;
-            if (!p.partial_mode) {
+            if (p.split) {
+                // ---- split mode: merge the two slots' partial states (FA.cu:575-597) through shared memory ----
+                // Row r of slot 1's un-normalised fp32 O travels in the four (D=64: two) 128-byte lines "row r" of the
+                // item's two Q tile buffers, 16-byte chunks XOR-swizzled by r & 7 like every other tile here; slot 0's
+                // thread r reads them back and then writes its fp16 output row over lines it has already consumed.
+                const uint32_t buf = sQ + ((it & 1u) * 2) * C::kTileBytes;
+                const uint32_t ml_slot = smem_base + C::kMlOffset + row_in_tile * 8;
+                auto line_addr = [&](int c4) {      // c4: index of a 16-byte chunk of the row's fp32 data (4 floats)
+                    const int line = c4 >> 3;       // 8 chunks per 128-byte line; lines: buf0.panel0, buf0.panel1, buf1.panel0, ...
+                    return buf + (line / C::kPanels) * C::kTileBytes + (line % C::kPanels) * C::kPanelBytes + row_in_tile * 128 +
+                           (((c4 & 7) ^ (row_in_tile & 7)) << 4);
+                };
+                if (t == 1) {
+                    if (n_t > 0) {
+#pragma unroll
+                        for (int c = 0; c < D; c += 32) {
+                            uint32_t o[32];
+                            tmem_ld_x32(tO + c, o);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) st_shared_v4(line_addr((c + i) >> 2), o[i], o[i + 1], o[i + 2], o[i + 3]);
+                        }
+                        st_shared_v2(ml_slot, __float_as_uint(m_ref), __float_as_uint(l_run));
+                        tc_fence_before();
+                        bar_arrive(1 + (warp & 3), 64);          // hand-over to warp (warp & 3) of slot 0: same 32 rows
+                    }
+                    continue;                                    // slot 1 neither stores nor stages
+                }
+                float w0 = 1.f, w1 = 0.f, l_tot = l_run;
+                const bool have1 = wi.n1 > 0;
+                if (have1) {
+                    bar_sync(1 + (warp & 3), 64);
+                    float m1, l1;
+                    ld_shared_v2f(ml_slot, m1, l1);
+                    const float m_max = fmaxf(m_ref, m1);
+                    w0 = (m_ref == -INFINITY) ? 0.f : ex2_approx((m_ref - m_max) * p.scale_log2);
+                    w1 = (m1 == -INFINITY) ? 0.f : ex2_approx((m1 - m_max) * p.scale_log2);
+                    l_tot = l_run * w0 + l1 * w1;
+                }
+                const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;      // FA.cu:502-503, 590
+                const float s0 = w0 * inv, s1 = w1 * inv;
+                const uint32_t stage = buf + row_in_tile * 128;
+#pragma unroll
+                for (int c = 0; c < D; c += 32) {
+                    uint32_t o[32];
+                    if (n_t > 0) {
+                        tmem_ld_x32(tO + c, o);
+                        tmem_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) o[i] = 0u;
+                    }
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) f[i] = __uint_as_float(o[i]) * s0;
+                    if (have1) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 x = ld_shared_v4f(line_addr((c + i) >> 2));
+                            f[i] += x.x * s1; f[i + 1] += x.y * s1; f[i + 2] += x.z * s1; f[i + 3] += x.w * s1;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        const int col = c + i;
+                        const uint32_t addr = stage + (col >> 6) * C::kPanelBytes + ((((col & 63) >> 3) ^ (row_in_tile & 7)) << 4);
+                        st_shared_v4(addr, pack_16x2<kBF16>(f[i], f[i + 1]), pack_16x2<kBF16>(f[i + 2], f[i + 3]),
+                                     pack_16x2<kBF16>(f[i + 4], f[i + 5]), pack_16x2<kBF16>(f[i + 6], f[i + 7]));
+                    }
+                }
+                fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
+            } else if (!p.partial_mode) {
                 const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;   // FA.cu:502-503
                 // fp16 row -> staging tile = this item's Q tile buffer (every QK^T of the item has retired:
                 // o_full covers them), 16-byte chunks XOR-swizzled by row & 7 as TMA expects for SWIZZLE_128B
@@ -1198,6 +1356,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             // it cannot complete twice before the store warp has seen the first completion, because the
             // slot's next use needs the Q load that the store warp itself releases.
             if (lane == 0) mbar_arrive(bar_o_staged + 8 * ((it & 1u) * 2 + t));
+#ifdef FA_TIMING
+            if (lane == 0 && (warp & 3) == 0) {
+                atomicAdd(&g_timing[14 + t], (unsigned long long)(clock64() - ti_ep));
+                atomicAdd(&g_timing[16 + t], (unsigned long long)(clock64() - ti0));   // whole item
+            }
+#endif
         }
     }
 
@@ -1259,10 +1423,13 @@ __global__ void fa_merge_kernel(const float* __restrict__ o_partial, const float
     const long long r = idx / per_row;
     if (r >= rows) return;
     const int c = (int)(idx % per_row) * 4;
+    // both loops unrolled by 4: the loads of four partial states are in flight together (the merge is pure HBM traffic)
     float m_max = -FLT_MAX;
+#pragma unroll 4
     for (int s = 0; s < splits; s++) m_max = fmaxf(m_max, ml[((long long)s * rows + r) * 2]);
     float l = 0.f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int s = 0; s < splits; s++) {
         const float m_s = ml[((long long)s * rows + r) * 2];
         const float l_s = ml[((long long)s * rows + r) * 2 + 1];

@@ -1,6 +1,6 @@
 """Burst-regime A/B of library builds over several shapes in ONE process (short runs separated by idle gaps).
    python tests/harness/ab_shapes.py [--env K=V ...] lib1.so lib2.so ... -- B,H,N,D,causal ...
-   A lib argument may carry environment settings for the work decomposition: path.so@ITEM_TILES=1"""
+   A lib argument may carry environment settings for the work decomposition: path.so@SPLIT=1"""
 import ctypes
 import os
 import sys
@@ -17,8 +17,8 @@ for a in libs_arg:
     L = ctypes.CDLL(os.path.abspath(path))
     L.flash_attn_fwd.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_void_p]
     L.flash_attn_fwd.restype = ctypes.c_int
-    if hasattr(L, "flash_attn_debug_set_item_tiles"):
-        L.flash_attn_debug_set_item_tiles.argtypes = [ctypes.c_int]
+    if hasattr(L, "flash_attn_debug_set_split"):
+        L.flash_attn_debug_set_split.argtypes = [ctypes.c_int]
     libs.append((os.path.basename(path) + ("@" + tag if tag else ""), L, tag))
 shapes = [tuple(int(x) for x in s.split(",")) for s in shapes_arg]
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -33,8 +33,8 @@ for (B, H, N, D, causal) in shapes:
     cold = {n: [] for n, _, _ in libs}
     for rnd in range(5):
         for name, L, tag in libs:
-            if tag and hasattr(L, "flash_attn_debug_set_item_tiles"):
-                L.flash_attn_debug_set_item_tiles(int(tag.split("=")[1]))
+            if tag and hasattr(L, "flash_attn_debug_set_split"):
+                L.flash_attn_debug_set_split(int(tag.split("=")[1]))      # @SPLIT=0 pair items, @SPLIT=1 split mode, @SPLIT=-1 automatic
             for _ in range(3):
                 assert L.flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, D, causal, st) == 0
             torch.cuda.synchronize()

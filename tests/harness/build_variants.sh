@@ -3,7 +3,7 @@
 set -e
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 mkdir -p build
-for v in "default:" "stream:-DFA_STREAM" "single:-DFA_SINGLE_TILE_MODE" "poly3:-DFA_POLY_LONG=3" "d64poly1:-DFA_POLY_D64=1" "d64poly3:-DFA_POLY_D64=3" $EXTRA_VARIANTS; do
+for v in "default:" "stream:-DFA_STREAM" "timing:-DFA_TIMING -DFA_TIMING_ALL" $EXTRA_VARIANTS; do
   n=${v%%:*}; f=${v#*:}
   $NV $f -shared flash_attention_cuda_b200/csrc/fa_api.cu -o build/lib_$n.so &
 done
@@ -13,3 +13,4 @@ for v in "base:" "stream:-DBENCH_STREAM"; do
 done
 wait
 ls -la build/lib_*.so build/softmax_bench_*
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build/softmax_half_bench tests/harness/micro/softmax_half_bench.cu

@@ -34,6 +34,11 @@ for t in range(2):
     w, b, n = (buf[t * 3 + i] for i in range(3))
     if n:
         print(f"  tile {t}: wait-for-S {w / n:7.1f} cyc  S->P {b / n:7.1f} cyc  period {(w + b) / n:7.1f}  ({n} sampled tiles)")
+for t in range(2):
+    if buf[9 + t * 2]:
+        n_it = buf[9 + t * 2]
+        print(f"  tile {t}: item start -> first S {buf[8 + t * 2] / n_it:8.0f} cyc   epilogue {buf[14 + t] / n_it:7.0f} cyc   whole item {buf[16 + t] / n_it:9.0f} cyc"
+              f"   kernel start -> first S of the CTA's first item {buf[12 + t] / max(1, buf[22]):8.0f} cyc   ({n_it} items)")
 c, ns, n = buf[20], buf[21], buf[22]
 if n:
     print(f"  CTA lifetime: {c / n:.0f} cycles = {ns / n / 1e3:.1f} us -> SM clock {c / ns * 1e3:.0f} MHz; kernel {ms * 1e3:.1f} us")

@@ -125,6 +125,41 @@ def test_score_steps_at_half_tile_boundaries(fa, D, step_at, jump):
         gate(gpu_attention(fa, q, k, v, causal), _oracle.attention(q, k, v, causal), f"D{D} step@{step_at} causal={causal}")
 
 
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("B,H,N,D,causal", [(1, 2, 1, 128, 1), (1, 3, 127, 128, 0), (2, 2, 129, 64, 1), (1, 4, 300, 128, 1),
+                                            (1, 2, 640, 128, 0), (2, 1, 1000, 64, 0), (1, 2, 1536, 128, 1), (1, 1, 2049, 128, 1)])
+def test_pair_items_and_split_mode_both_match_the_oracle(fa, split, B, H, N, D, causal):
+    """The launcher picks split mode (one Q tile per item, KV tiles alternating between the two tile slots, partial states
+    merged in shared memory with the FA.cu:575-597 algebra) for few / short items; force each decomposition in turn."""
+    q, k, v = normal((B, H, N, D), 11 + N)
+    fa.set_split(split)
+    try:
+        out = gpu_attention(fa, q, k, v, causal)
+    finally:
+        fa.set_split(None)
+    gate(out, _oracle.attention(q, k, v, causal), f"split={split} B{B} H{H} N{N} D{D} causal={causal}")
+
+
+def test_split_mode_merges_slots_whose_references_differ(fa):
+    """Even KV tiles hold small scores, odd ones large (and vice versa): the two slots end with very different reference
+    maxima and the merge weights w = exp(m_s - max m) do the work."""
+    N, D = 1024, 128
+    rng = np.random.default_rng(5)
+    level = np.where((np.arange(N) // 128) % 2 == 0, 0.0, 9.0)          # nats, per key
+    q = np.ones((1, 2, N, D), np.float32)
+    q[:, 1] *= -1.0                                                      # second head: the even tiles win
+    k = np.broadcast_to((level / np.sqrt(D))[None, None, :, None], (1, 2, N, D)).astype(np.float32)
+    k = k + rng.standard_normal((1, 2, N, D), dtype=np.float32) * 0.02
+    v = rng.standard_normal((1, 2, N, D), dtype=np.float32) * 0.5
+    q, k, v = q.astype(np.float16), k.astype(np.float16), v.astype(np.float16)
+    fa.set_split(True)
+    try:
+        for causal in (0, 1):
+            gate(gpu_attention(fa, q, k, v, causal), _oracle.attention(q, k, v, causal), f"causal={causal}")
+    finally:
+        fa.set_split(None)
+
+
 def test_causal_row0_equals_v0(fa):
     q, k, v = _oracle.fill_ref_rand((1, 8, 300, 128), 42)
     out = gpu_attention(fa, q, k, v, 1)

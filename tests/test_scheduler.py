@@ -99,25 +99,22 @@ def test_head_groups_are_equal_sized():
     assert heads == [list(range(0, 7)), list(range(7, 14)), list(range(14, 20))]
 
 
-def test_single_tile_work_items_cover_every_tile_too(tmp_path):
-    """Experimental single-tile work items (a -DFA_SINGLE_TILE_MODE build + FLASH_ATTN_B200_ITEM_TILES=1): the same
-    decomposition tests in that mode.  The product build ignores the variable."""
-    import os
-    import shutil
-    import subprocess
-    import sys
-    assert fa.tiles_per_item(128) == 2
-    if shutil.which("nvcc") is None:
-        pytest.skip("nvcc not available")
-    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    lib = str(tmp_path / "libfa_single.so")
-    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-Xcompiler", "-fPIC",
-                    "-DFA_SINGLE_TILE_MODE", "-shared", os.path.join(repo, "flash_attention_cuda_b200", "csrc", "fa_api.cu"),
-                    "-o", lib], check=True, cwd=repo)
-    env = dict(os.environ, FLASH_ATTN_B200_ITEM_TILES="1", FLASH_ATTN_B200_LIB=lib)
-    code = ("import flash_attention_cuda_b200 as fa, sys; assert fa.tiles_per_item(128) == 1; "
-            "it = fa.work_item(0, 1, 32, 1024, 1024, 128, True); assert it['total'] == 256 and it['n1'] == 0, it")
-    subprocess.run([sys.executable, "-c", code], env=env, check=True, cwd=repo)
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
-                        "every_q_tile or masked_tiles or triangular"], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+@pytest.mark.parametrize("N", [1, 127, 128, 129, 256, 257, 1000, 1024, 2048])
+@pytest.mark.parametrize("causal", [False, True])
+def test_split_mode_covers_every_q_tile_and_every_kv_tile_once(N, causal):
+    """Split mode (short sequences): an item is ONE Q tile; slot 0 takes its KV tiles 0, 2, 4, ... and slot 1 the odd ones."""
+    B, H = 2, 3
+    total = fa.work_item(0, B, H, N, N, 128, causal, split=True)["total"]
+    its = [fa.work_item(w, B, H, N, N, 128, causal, split=True) for w in range(total)]
+    nq_tiles = (N + 127) // 128
+    assert total == B * H * nq_tiles
+    seen = set()
+    for it in its:
+        assert (it["bh"], it["q0"]) not in seen and it["q0"] % 128 == 0 and it["q0"] < N
+        seen.add((it["bh"], it["q0"]))
+        last_row = min(it["q0"] + 127, N - 1)
+        want = (min(N, last_row + 1) + 127) // 128 if causal else (N + 127) // 128
+        assert it["n0"] + it["n1"] == want and it["n0"] == (want + 1) // 2 and it["n1"] == want // 2
+    assert len(seen) == total
+    w = [it["n"] for it in its]
+    assert w == sorted(w, reverse=True)      # heavy-first (one L2 group at these sizes)
