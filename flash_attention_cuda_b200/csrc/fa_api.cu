@@ -97,7 +97,11 @@ int set_kernel_attrs() {
                                      fa::Cfg<D>::kSmemBytes);
 }
 // exp2 on the FMA pipe for 1 pair in 4 only where it pays: D = 128 and at least 32 KV tiles (fa_fwd_sm100.cuh)
-bool use_poly(int D, int Nkv) { return D == 128 && Nkv >= 4096; }
+#ifndef FA_POLY_MIN_N
+#define FA_POLY_MIN_N 4096
+#endif
+// (without a causal mask it already pays from N = 512 on: +1-3 %, profiles/r02_c6_polyall_ab.log)
+bool use_poly(int D, int Nkv, int causal = 1) { return D == 128 && Nkv >= (causal ? FA_POLY_MIN_N : 512); }
 // Per-device setup, on the first call on that device (and again after flash_attn_destroy).  Re-entrant from
 // several host threads (one per GPU in a multi-GPU harness): guarded by the device's mutex.
 DeviceState* device_state(int* err) {
@@ -316,11 +320,11 @@ int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaS
     if (rc != FA_OK) return rc;
     if (bf16) {
         if (D == 64) return launch<64, kPolyD64, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        return use_poly(D, p.Nkv) ? launch<128, kPolyLong, true>(st, t.tq, t.tk, t.tv, t.to, p, stream)
+        return use_poly(D, p.Nkv, p.causal) ? launch<128, kPolyLong, true>(st, t.tq, t.tk, t.tv, t.to, p, stream)
                                   : launch<128, 0, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
     }
     if (D == 64) return launch<64, kPolyD64>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-    return use_poly(D, p.Nkv) ? launch<128, kPolyLong>(st, t.tq, t.tk, t.tv, t.to, p, stream)
+    return use_poly(D, p.Nkv, p.causal) ? launch<128, kPolyLong>(st, t.tq, t.tk, t.tv, t.to, p, stream)
                               : launch<128, 0>(st, t.tq, t.tk, t.tv, t.to, p, stream);
 }
 
@@ -482,14 +486,13 @@ int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho
 }
 
 int flash_attn_get_kernel_info(int B, int H, int N, int D, int causal, flash_attn_kernel_info* info) {
-    (void)causal;
     if (!info) return FA_ERR_NULL_PTR;
     if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
     if (B < 1 || H < 1 || N < 1) return FA_ERR_BAD_SHAPE;
     memset(info, 0, sizeof *info);
     cudaFuncAttributes attr;
     cudaError_t e = D == 64            ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<64, kPolyD64>)
-                    : use_poly(D, N) ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, kPolyLong>)
+                    : use_poly(D, N, causal) ? cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, kPolyLong>)
                                      : cudaFuncGetAttributes(&attr, fa::fa_fwd_kernel<128, 0>);
     if (e != cudaSuccess) return (int)e;
     int err = 0;
