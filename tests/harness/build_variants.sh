@@ -3,7 +3,7 @@
 set -e
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 mkdir -p build
-for v in "default:" "stream:-DFA_STREAM" "timing:-DFA_TIMING -DFA_TIMING_ALL" "polyall:-DFA_POLY_MIN_N=0" $EXTRA_VARIANTS; do
+for v in "default:" "stream:-DFA_STREAM" "timing:-DFA_TIMING" $EXTRA_VARIANTS; do
   n=${v%%:*}; f=${v#*:}
   $NV $f -shared flash_attention_cuda_b200/csrc/fa_api.cu -o build/lib_$n.so &
 done
