@@ -139,9 +139,6 @@ def lib() -> ctypes.CDLL:
         L.flash_attn_debug_set_split.restype = None
         L.flash_attn_debug_uses_split.argtypes = [ci, ci, ci, ci]
         L.flash_attn_debug_uses_split.restype = ci
-    if hasattr(L, "flash_attn_debug_set_coop"):
-        L.flash_attn_debug_set_coop.argtypes = [ci]
-        L.flash_attn_debug_set_coop.restype = None
     if hasattr(L, "flash_attn_debug_tiles_per_item"):   # absent from archived A/B builds of older kernels
         L.flash_attn_debug_tiles_per_item.argtypes = [ci]
         L.flash_attn_debug_tiles_per_item.restype = ci
@@ -360,12 +357,6 @@ def work_item(w: int, B: int, H: int, Nq: int, Nkv: int, D: int, causal: bool, s
 def set_split(mode) -> None:
     """Work decomposition of flash_attn_fwd from now on: None = automatic, False = pair items, True = split mode."""
     lib().flash_attn_debug_set_split(-1 if mode is None else (1 if mode else 0))
-
-
-def set_coop(mode) -> None:
-    """Softmax form of pair-mode launches from now on: None = the build's default, False = one row per thread,
-    True = cooperative (the two warps of a lane quadrant share every S tile)."""
-    lib().flash_attn_debug_set_coop(-1 if mode is None else (1 if mode else 0))
 
 
 def uses_split(B: int, H: int, N: int, causal: bool) -> bool:

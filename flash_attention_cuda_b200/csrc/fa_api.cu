@@ -93,12 +93,8 @@ void load_encode_fn() {
 
 template <int D, int kPoly, bool kBF16 = false>
 int set_kernel_attrs() {
-    int r = (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D, kPoly, kBF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      fa::Cfg<D>::kSmemBytes);
-    if (r == 0)
-        r = (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D, kPoly, kBF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      fa::Cfg<D>::kSmemBytes);
-    return r;
+    return (int)cudaFuncSetAttribute(fa::fa_fwd_kernel<D, kPoly, kBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fa::Cfg<D>::kSmemBytes);
 }
 // exp2 on the FMA pipe for 1 pair in 4 only where it pays: D = 128 and at least 32 KV tiles (fa_fwd_sm100.cuh)
 #ifndef FA_POLY_MIN_N
@@ -189,24 +185,6 @@ int validate(const void* q, const void* k, const void* v, const void* o, int B, 
     return FA_OK;
 }
 
-// Cooperative softmax (fa_fwd_sm100.cuh: coop_softmax_tile): the two softmax warps of a lane quadrant share every S tile.
-// FLASH_ATTN_B200_COOP = 0 / 1 forces it off / on; flash_attn_debug_set_coop overrides at run time.
-#ifndef FA_COOP_DEFAULT
-#define FA_COOP_DEFAULT 0
-#endif
-std::atomic<int> g_coop_override{-2};
-bool use_coop(const fa::Params& p) {
-    int o = g_coop_override.load(std::memory_order_relaxed);
-    if (o == -2) {
-        const char* e = getenv("FLASH_ATTN_B200_COOP");
-        o = e && (e[0] == '0' || e[0] == '1') ? e[0] - '0' : -1;
-        g_coop_override.store(o, std::memory_order_relaxed);
-    }
-    if (p.split) return false;            // split mode keeps one row per thread
-    if (o >= 0) return o == 1;
-    return FA_COOP_DEFAULT != 0;
-}
-
 // Split mode (fa_fwd_sm100.cuh): one Q tile per work item, its KV tiles alternating between the CTA's two tile slots.
 // Used where pair items are too few to keep the machine busy (use_split below).
 // FLASH_ATTN_B200_SPLIT = 0 / 1 forces it off / on (A/B runs); flash_attn_debug_set_split overrides at run time.
@@ -259,7 +237,7 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
     return p;
 }
 
-template <int D, int kPoly, bool kBF16 = false, bool kCoop = false>
+template <int D, int kPoly, bool kBF16 = false>
 int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
            const CUtensorMap& to, fa::Params p, cudaStream_t stream) {
     int avail = st->num_sms - g_sm_margin.load(std::memory_order_relaxed);
@@ -289,7 +267,7 @@ int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D, kPoly, kBF16, kCoop>, tq, tk, tv, to, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fa::fa_fwd_kernel<D, kPoly, kBF16>, tq, tk, tv, to, p);
     if (le != cudaSuccess) return (int)le;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();   // FA.cu:662
@@ -341,21 +319,14 @@ int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaS
     int rc = get_tmaps(st, q, k, v, p.partial_mode ? nullptr : (const void*)p.o, p, D, bf16, &t);
     if (rc != FA_OK) return rc;
     const bool poly = use_poly(D, p.Nkv, p.causal);
-    const int variant = (D == 64 ? 0 : poly ? 1 : 2) * 4 + (bf16 ? 2 : 0) + (use_coop(p) ? 1 : 0);
-    switch (variant) {
-        case 0: return launch<64, kPolyD64, false, false>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        case 1: return launch<64, kPolyD64, false, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        case 2: return launch<64, kPolyD64, true, false>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        case 3: return launch<64, kPolyD64, true, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        case 4: return launch<128, kPolyLong, false, false>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        case 5: return launch<128, kPolyLong, false, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        case 6: return launch<128, kPolyLong, true, false>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        case 7: return launch<128, kPolyLong, true, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        case 8: return launch<128, 0, false, false>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        case 9: return launch<128, 0, false, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        case 10: return launch<128, 0, true, false>(st, t.tq, t.tk, t.tv, t.to, p, stream);
-        default: return launch<128, 0, true, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
+    if (bf16) {
+        if (D == 64) return launch<64, kPolyD64, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
+        return poly ? launch<128, kPolyLong, true>(st, t.tq, t.tk, t.tv, t.to, p, stream)
+                    : launch<128, 0, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
     }
+    if (D == 64) return launch<64, kPolyD64>(st, t.tq, t.tk, t.tv, t.to, p, stream);
+    return poly ? launch<128, kPolyLong>(st, t.tq, t.tk, t.tv, t.to, p, stream)
+                : launch<128, 0>(st, t.tq, t.tk, t.tv, t.to, p, stream);
 }
 
 }  // namespace
@@ -719,7 +690,6 @@ extern "C" int flash_attn_debug_tiles_per_item(int D) {
     if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
     return 2;
 }
-extern "C" void flash_attn_debug_set_coop(int mode) { g_coop_override.store(mode < -1 || mode > 1 ? -1 : mode, std::memory_order_relaxed); }
 // -1 automatic (use_split), 0 never, 1 always: which work decomposition flash_attn_fwd uses from now on (A/B runs, tests)
 extern "C" void flash_attn_debug_set_split(int mode) { g_split_override.store(mode < -1 || mode > 1 ? -1 : mode, std::memory_order_relaxed); }
 // 1 when flash_attn_fwd would run this shape in split mode on the current device

@@ -113,10 +113,10 @@ struct Cfg {
     static constexpr int kSmemQ = 4 * kTileBytes;
     static constexpr int kSmemKV = kStages * kTileBytes;
     static constexpr int kBarOffset = kSmemQ + kSmemKV;
-    static constexpr int kNumBars = 4 + 2 * kStages + 14 + 4 + 4 + 8;          // + 8: row-max exchange of the cooperative softmax
+    static constexpr int kNumBars = 4 + 2 * kStages + 14 + 4 + 4;
     static constexpr int kMlOffset = kBarOffset + kNumBars * 8 + 32;           // +32: tmem slot, scheduler slots
-    // 2 KB hand-over area: (m, l) of tile slot 1 in split mode, or [tile][column half][row] floats of the cooperative softmax
-    static constexpr int kXchBytes = 2 * 2 * kBlockM * 4;
+    // hand-over area of split mode: (m, l) of tile slot 1, one pair per row
+    static constexpr int kXchBytes = kBlockM * 8;
     // SWIZZLE_128B tiles need a 1024-byte aligned base; the dynamic window is that aligned on sm_100 in practice, the
     // slack (whatever is left of the 227 KB, at most 1 KB) covers a base that is not, and the kernel checks
     static constexpr int kSmemMax = 232448;
@@ -205,12 +205,6 @@ __host__ __device__ inline WorkItem decode_work(int w, const Params& p) {
 
 #ifdef FA_TIMING
 __device__ unsigned long long g_timing[64];
-// phase probe of the cooperative softmax (thread 0 only): adds the cycles since the previous probe to counter 32 + k
-#define FA_PROBE(k) do { if (threadIdx.x == 0) { const long long c_ = clock64(); atomicAdd(&g_timing[32 + (k)], (unsigned long long)(c_ - tp_)); tp_ = c_; } } while (0)
-#define FA_PROBE_START() long long tp_ = clock64()
-#else
-#define FA_PROBE(k) do {} while (0)
-#define FA_PROBE_START() do {} while (0)
 #endif
 
 // ptxas schedules a basic block as a whole and gives the F2FP + tcgen05.st of the first piece of P the lowest priority
@@ -721,139 +715,7 @@ __device__ __forceinline__ bool softmax_tile_stream(const Params& p, uint32_t tS
     return true;
 }
 
-// ---- cooperative softmax: the two softmax warps of a lane quadrant work on the SAME S tile, 64 columns each ----
-// One thread per row makes a tile's S -> P step ~1340 cycles of one warp's issue stream (profiles/r02_softmax_hot_loop.sass.txt),
-// and the two Q tiles of a work item need that twice per period on every sub-partition: 2 x 1340 = 2680 cycles for 2048 cycles
-// of tensor work -- the measured period.  Here warps q and q+4 (same sub-partition, same 32 TMEM lanes) split every tile's
-// columns, first tile 0's, then tile 1's: a tile's S -> P latency halves (tests/harness/micro/softmax_half_bench.cu: 924-1113
-// cycles), the two tiles' softmax phases no longer compete for the sub-partition, and each runs under the other tile's MMAs.
-// The two threads of a row share the row's reference max (bit-identical in both: every update is computed from the same
-// exchanged values) but keep separate partial row sums:
-//   * first tile of an item: the half-row maxima are exchanged through shared memory before the exponentials;
-//   * later tiles: exponentials run against the current reference while the half-row maxima are exchanged (posted before,
-//     collected after the exponentials); a row that outgrew the reference by more than 2^kHardThreshold makes both warps
-//     rescale their halves of O and redo the tile (S is still intact: P is stored after the check);
-//   * lazy update of the reference (2^kRescaleThreshold) at the end of the tile, behind the tile's own PV.
-// P piece h (keys 64h .. 64h+63) is stored over the first 32 of the warp's own 64 S columns, so the warps never touch each
-// other's columns; the MMA warp reads piece 1 from columns [64,96).
-template <int D, bool kMask, int kPoly, bool kBF16>
-__device__ __forceinline__ void coop_softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t x_mine, uint32_t x_other,
-                                                  uint32_t bar_x, uint32_t& x_phase, uint32_t bar_p, uint32_t bar_o_full,
-                                                  int lim_local, bool first, bool last, uint32_t pv_count, float& m_ref,
-                                                  float& l_part) {
-    // The two warps of a quadrant read their halves of S at the same time and share the quadrant's TMEM read port
-    // (64 B/clk: 256 cycles for the 16 KB of a tile quadrant): the second chunk of 32 columns lands under the first one's work.
-    uint32_t a[32], b[32];
-    FA_PROBE_START();
-    tmem_ld_x32(tS, a);
-    tmem_wait_ld();
-    tmem_ld_x32(tS + 32, b);
-    FA_PROBE(0);
-    mask_chunk<kMask>(a, 0, lim_local);
-    const float mx_a = max_chunk(a);
-    // exchange with the thread that owns the other 64 columns of this row
-    auto post = [&](float v) {
-        st_shared_f32(x_mine, v);
-        __syncwarp();
-        if (lane_id() == 0) mbar_arrive(bar_x);
-    };
-    auto collect = [&]() {
-        mbar_wait(bar_x, x_phase, 43);
-        x_phase ^= 1u;
-        return ld_shared_f32(x_other);
-    };
-    const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
-    uint64_t sum_a = 0ull, sum_b = 0ull;
-    uint32_t pk[32];
-    auto shift2 = [&]() {
-        const float neg = -((m_ref == -INFINITY) ? 0.0f : m_ref) * p.scale_log2;
-        return pack_f32x2(neg, neg);
-    };
-    auto rescale_o = [&](float alpha) {
-        const uint64_t alpha2 = pack_f32x2(alpha, alpha);
-#pragma unroll 1
-        for (int cc = 0; cc < D / 2; cc += 32) {
-            uint32_t o[32];
-            tmem_ld_x32(tO + cc, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                float lo, hi;
-                unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), lo, hi);
-                o[i] = __float_as_uint(lo);
-                o[i + 1] = __float_as_uint(hi);
-            }
-            tmem_st_x32(tO + cc, o);
-        }
-    };
-    float m_tile;
-    if (first) {
-        tmem_wait_ld();
-        mask_chunk<kMask>(b, 32, lim_local);
-        const float m_h = fmaxf(mx_a, max_chunk(b));
-        post(m_h);
-        m_tile = fmaxf(m_h, collect());
-        m_ref = m_tile;                              // -inf for a row that sees no key of this tile
-        const uint64_t neg2 = shift2();
-        exp_half<kPoly, kBF16, 32>(a, pk, scale2, neg2, sum_a, sum_b);
-        exp_half<kPoly, kBF16, 32>(b, pk + 16, scale2, neg2, sum_a, sum_b);
-    } else {
-        // against the row's current reference; the half-row maxima cross over under the second chunk's exponentials
-        const uint64_t neg2 = shift2();
-        exp_half<kPoly, kBF16, 32>(a, pk, scale2, neg2, sum_a, sum_b);
-        FA_PROBE(1);
-        tmem_wait_ld();
-        mask_chunk<kMask>(b, 32, lim_local);
-        const float m_h = fmaxf(mx_a, max_chunk(b));
-        post(m_h);
-        FA_PROBE(2);
-        exp_half<kPoly, kBF16, 32>(b, pk + 16, scale2, neg2, sum_a, sum_b);
-        FA_PROBE(3);
-        m_tile = fmaxf(m_h, collect());
-        FA_PROBE(4);
-        const bool bad = (m_tile - m_ref) * p.scale_log2 > kHardThreshold;     // NaN (-inf - -inf) -> false
-        if (__any_sync(0xffffffffu, bad)) {          // same verdict in the partner warp: it sees the same rows' values
-            const float m_new = fmaxf(m_ref, m_tile);
-            const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
-            mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 44);     // O_t holds PV(0..j-1): the last one must have retired
-            tc_fence_after();
-            rescale_o(alpha);
-            l_part *= alpha;
-            m_ref = m_new;
-            tmem_ld_x32(tS, a);                      // S is intact: P is stored below
-            tmem_ld_x32(tS + 32, b);
-            tmem_wait_ld();
-            mask_chunk<kMask>(a, 0, lim_local);
-            mask_chunk<kMask>(b, 32, lim_local);
-            const uint64_t neg2b = shift2();
-            sum_a = 0ull;
-            sum_b = 0ull;
-            exp_half<kPoly, kBF16, 32>(a, pk, scale2, neg2b, sum_a, sum_b);
-            exp_half<kPoly, kBF16, 32>(b, pk + 16, scale2, neg2b, sum_a, sum_b);
-        }
-    }
-    tmem_st_x32(tS, pk);
-    tmem_wait_st();
-    tc_fence_before();
-    __syncwarp();
-    if (lane_id() == 0) mbar_arrive(bar_p);          // one arrival per warp; piece h completes with the four quadrants
-    FA_PROBE(5);
-    float a0, a1;
-    unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
-    l_part += a0 + a1;
-    const float m_new = fmaxf(m_ref, m_tile);
-    const bool need = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;
-    if (!last && __any_sync(0xffffffffu, need)) {
-        const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
-        mbar_wait(bar_o_full, pv_count & 1u, 42);    // PV of THIS tile retired: O_t is quiescent until our next P
-        tc_fence_after();
-        rescale_o(alpha);
-        l_part *= alpha;
-        m_ref = m_new;
-    }
-}
-
-template <int D, int kPoly, bool kBF16 = false, bool kCoop = false>
+template <int D, int kPoly, bool kBF16 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
@@ -879,8 +741,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t bar_o_staged = bar_o_half + 16;                // [Q slot][tile] softmax warps -> store warp
     const uint32_t bar_sched_full = bar_o_staged + 32;            // [2] work-index slots, producer -> everyone
     const uint32_t bar_sched_empty = bar_sched_full + 16;         // [2]
-    const uint32_t bar_xch = bar_sched_empty + 16;                // [tile][lane quadrant] row-max exchange (cooperative softmax)
-    const uint32_t tmem_slot = bar_xch + 64;
+    const uint32_t tmem_slot = bar_sched_empty + 16;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     volatile int* sched_w = reinterpret_cast<volatile int*>(tmem_slot_ptr + 2);   // [2]
 
@@ -911,10 +772,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 mbar_init(bar_p_full + 32 * t + 8 * part, 4);   // one arrival per softmax warp of the tile, per piece of P
             mbar_init(bar_o_full + 8 * t, 1);
             mbar_init(bar_o_half + 8 * t, 1);
-            mbar_init(bar_o_staged + 8 * t, kCoop ? 8 : 4);       // one arrival per softmax warp of the tile,
-            mbar_init(bar_o_staged + 8 * (2 + t), kCoop ? 8 : 4); // per Q slot (cooperative softmax: all eight warps stage every tile)
+            mbar_init(bar_o_staged + 8 * t, 4);       // one arrival per softmax warp of the tile,
+            mbar_init(bar_o_staged + 8 * (2 + t), 4); // per Q slot
         }
-        for (int i = 0; i < 8; i++) mbar_init(bar_xch + 8 * i, 2);   // the two warps that share a lane quadrant
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_sched_full + 8 * i, 1);
             mbar_init(bar_sched_empty + 8 * i, 10);   // MMA warp + 8 softmax warps + store warp
@@ -1056,9 +916,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 if (elect_one()) {
 #pragma unroll
                     for (int ks = p_part_ks(part); ks < p_part_ks(part + 1); ks++)
-                        // P k-step ks = 8 TMEM columns; the cooperative softmax keeps keys 64-127 at columns [64,96) of S_t
-                        // (the columns their producer warp owns) instead of [32,64)
-                        umma_ts(tO, tP + ((kCoop && ks >= 4) ? 64 + (ks - 4) * 8 : ks * 8), vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV | (kBF16 ? C::kBf16Operands : 0u),
+                        umma_ts(tO, tP + ks * 8, vdesc + (uint64_t)((ks * 16 * 128) >> 4), C::kIdescPV | (kBF16 ? C::kBf16Operands : 0u),
                                 (accumulate || ks > 0) ? 1u : 0u);
 #ifdef FA_SUM_GUARD
                     if (part == 0) umma_commit(bar_oh);
@@ -1230,193 +1088,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
     } else {
         setmaxnreg_inc<kRegsSoftmax>();
-        if constexpr (kCoop) {
-        // =============================== cooperative softmax / correction / epilogue ===============================
-        // (pair-mode items only: the launcher never combines this instantiation with split mode)
-        const int h = warp >> 2;                               // column half of every S / O tile this warp owns
-        const int quad = warp & 3;
-        const int row_in_tile = quad * 32 + lane;              // TMEM lane == S/O row
-        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        const uint32_t xch = smem_base + C::kMlOffset;         // [tile][half][row] floats
-        uint32_t s_phase[2] = {0u, 0u}, pv_count[2] = {0u, 0u}, x_phase[2] = {0u, 0u};
-        for (uint32_t it = 0;; ++it) {
-            const int w = next_work(it);
-            if (w < 0) break;
-            const WorkItem wi = decode_work(w, p);
-            const int n_t[2] = {wi.n0, wi.n1};
-            float m_ref[2] = {-INFINITY, -INFINITY}, l_part[2] = {0.f, 0.f};
-            int lim[2];
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-                const int row = wi.q0 + t * kBlockM + row_in_tile;
-                long long lim_ll = p.causal ? (long long)row + p.shift + 1 : (long long)p.Nkv;   // keys [0, lim) are visible
-                if (lim_ll > p.Nkv) lim_ll = p.Nkv;
-                if (lim_ll < 0) lim_ll = 0;
-                lim[t] = (int)lim_ll;
-            }
-            for (int j = 0; j < wi.nkv; j++) {
-#pragma unroll
-                for (int t = 0; t < 2; t++) {
-                    if (j >= n_t[t]) continue;
-#ifdef FA_TIMING
-                    const long long tw0 = clock64();
-#endif
-                    mbar_wait(bar_s_full + 8 * t, s_phase[t], 20 + t);
-                    s_phase[t] ^= 1u;
-                    tc_fence_after();
-#ifdef FA_TIMING
-                    const long long tw1 = clock64();
-#endif
-                    const int q_start = wi.q0 + t * kBlockM;
-                    const int k0 = j * kBlockN;
-                    const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
-                    const uint32_t tS = tmem_base + lane_base + (t ? C::kTmemS1 : C::kTmemS0) + 64 * h;
-                    const uint32_t tO = tmem_base + lane_base + (t ? C::kTmemO1 : C::kTmemO0) + (D / 2) * h;
-                    const uint32_t x_mine = xch + ((t * 2 + h) * kBlockM + row_in_tile) * 4;
-                    const uint32_t x_other = xch + ((t * 2 + (h ^ 1)) * kBlockM + row_in_tile) * 4;
-                    const uint32_t bx = bar_xch + 8 * (t * 4 + quad);
-                    const uint32_t bp = bar_p_full + 32 * t + 8 * h;
-                    const bool last = j + 1 == n_t[t];
-                    if (need_mask)
-                        coop_softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, x_mine, x_other, bx, x_phase[t], bp, bar_o_full + 8 * t,
-                                                                 lim[t] - k0 - 64 * h, j == 0, last, pv_count[t], m_ref[t], l_part[t]);
-                    else
-                        coop_softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, x_mine, x_other, bx, x_phase[t], bp, bar_o_full + 8 * t,
-                                                                  64, j == 0, last, pv_count[t], m_ref[t], l_part[t]);
-                    ++pv_count[t];
-#ifdef FA_TIMING
-                    if (lane == 0 && quad == 0 && h == 0 && j > 0 && (j & 7) == 0) {   // sampled: 1 tile in 8
-                        const long long tw2 = clock64();
-                        atomicAdd(&g_timing[t * 3 + 0], (unsigned long long)(tw1 - tw0));
-                        atomicAdd(&g_timing[t * 3 + 1], (unsigned long long)(tw2 - tw1));
-                        atomicAdd(&g_timing[t * 3 + 2], 1ull);
-                    }
-#endif
-                }
-            }
-            // ---- epilogue, tile 0 then tile 1: this warp's D/2 columns of O_t / l -> fp16 -> staging (or the partial format) ----
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-                if (t == 1 && !wi.tile1) continue;             // this Q tile does not exist (the store warp knows)
-                const int q_start = wi.q0 + t * kBlockM;
-                const int row = q_start + row_in_tile;
-                const uint32_t tO = tmem_base + lane_base + (t ? C::kTmemO1 : C::kTmemO0) + (D / 2) * h;
-                if (n_t[t] > 0) {
-                    mbar_wait(bar_o_full + 8 * t, (pv_count[t] - 1u) & 1u, 30 + t);
-                    tc_fence_after();
-                } else {
-                    mbar_wait(bar_q_full + 8 * (it & 1u), (it >> 1) & 1u, 32 + t);   // see the one-row-per-thread epilogue below
-                }
-                const bool row_ok = row < p.Nq;
-                const size_t grow = (size_t)wi.bh * p.Nq + row;
-                // the partial-state form reads the old (m, l) before the hand-over below and writes after it
-                float2 ml_old = make_float2(-FLT_MAX, 0.f);
-                if (p.partial_mode && p.accumulate && row_ok) ml_old = __ldcg(reinterpret_cast<const float2*>(p.ml + grow * 2));
-                // row sum = this warp's half + the partner warp's half (named barrier 5 + quad: warps quad and quad + 4)
-                const uint32_t x_mine = xch + ((t * 2 + h) * kBlockM + row_in_tile) * 4;
-                const uint32_t x_other = xch + ((t * 2 + (h ^ 1)) * kBlockM + row_in_tile) * 4;
-                st_shared_f32(x_mine, l_part[t]);
-                bar_sync(5 + quad, 64);
-                const float l_run = l_part[t] + ld_shared_f32(x_other);
-                bar_sync(5 + quad, 64);                        // both have read: the slots may be rewritten (next item's maxima)
-                if (!p.partial_mode) {
-                    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;   // FA.cu:502-503
-                    // D/2 = 64 columns = one 128-byte-swizzled panel of the staging tile (the item's idle Q tile buffer)
-                    const uint32_t stage = sQ + ((it & 1u) * 2 + t) * C::kTileBytes + ((D / 2) * h >> 6) * C::kPanelBytes + row_in_tile * 128;
-#pragma unroll
-                    for (int c = 0; c < D / 2; c += 32) {
-                        uint32_t o[32];
-                        if (n_t[t] > 0) {
-                            tmem_ld_x32(tO + c, o);
-                            tmem_wait_ld();
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; i++) o[i] = 0u;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            const int col = (D / 2) * h + c + i;
-                            const uint32_t addr = stage + ((((col & 63) >> 3) ^ (row_in_tile & 7)) << 4);
-                            const uint32_t v0 = pack_16x2<kBF16>(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
-                            const uint32_t v1 = pack_16x2<kBF16>(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-                            const uint32_t v2 = pack_16x2<kBF16>(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-                            const uint32_t v3 = pack_16x2<kBF16>(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-                            st_shared_v4(addr, v0, v1, v2, v3);
-                        }
-                    }
-                    fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
-                } else {
-                    // partial state (FA.cu:460-496), merge algebra of FA.cu:575-597 when accumulating; this warp's D/2 columns go
-                    // through its own slice of Q tile buffer h and leave it transposed (whole sectors per group of lanes)
-                    float m_out = (m_ref[t] == -INFINITY) ? -FLT_MAX : m_ref[t] * p.scale;
-                    float l_out = l_run;
-                    float w_new = 1.f, w_old = 0.f;
-                    if (p.accumulate && row_ok) {
-                        const float m_old = ml_old.x, l_old = ml_old.y;
-                        const float m_max = fmaxf(m_old, m_out);
-                        const float kLog2e = 1.4426950408889634f;
-                        w_old = (m_old <= -FLT_MAX) ? 0.f : ex2_approx((m_old - m_max) * kLog2e);
-                        w_new = (m_out <= -FLT_MAX) ? 0.f : ex2_approx((m_out - m_max) * kLog2e);
-                        l_out = l_old * w_old + l_run * w_new;
-                        m_out = m_max;
-                    }
-                    constexpr int kW = D / 2;                  // fp32 columns this warp owns
-                    constexpr int kCPR = kW / 4;               // 16-byte chunks per staged row = lanes per row on the way out
-                    constexpr int kRPI = 32 / kCPR;            // rows one warp instruction covers on the way out
-                    const uint32_t wstage = sQ + ((it & 1u) * 2 + h) * C::kTileBytes + (uint32_t)quad * (32 * kW * 4);
-                    const int warp_row0 = q_start + quad * 32;
-                    float* const gbase = p.o_partial + ((size_t)wi.bh * p.Nq + warp_row0) * D + h * kW;
-#pragma unroll
-                    for (int c = 0; c < kW; c += 32) {
-                        uint32_t o[32];
-                        if (n_t[t] > 0) {
-                            tmem_ld_x32(tO + c, o);
-                            tmem_wait_ld();
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; i++) o[i] = 0u;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const int ch = (c + i) >> 2;
-                            st_shared_v4(wstage + lane * (kW * 4) + ((ch ^ (lane & (kCPR - 1))) << 4),
-                                         __float_as_uint(__uint_as_float(o[i]) * w_new), __float_as_uint(__uint_as_float(o[i + 1]) * w_new),
-                                         __float_as_uint(__uint_as_float(o[i + 2]) * w_new), __float_as_uint(__uint_as_float(o[i + 3]) * w_new));
-                        }
-                    }
-                    __syncwarp();
-                    const int ch = lane & (kCPR - 1);
-                    float4 old[kCPR];
-#pragma unroll
-                    for (int i = 0; i < kCPR; i++) {
-                        const int rr = i * kRPI + lane / kCPR;          // row within this warp's 32
-                        old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.accumulate && warp_row0 + rr < p.Nq)
-                            old[i] = __ldcg(reinterpret_cast<const float4*>(gbase + (size_t)rr * D + ch * 4));
-                    }
-#pragma unroll
-                    for (int i = 0; i < kCPR; i++) {
-                        const int rr = i * kRPI + lane / kCPR;
-                        float4 v = ld_shared_v4f(wstage + rr * (kW * 4) + ((ch ^ (rr & (kCPR - 1))) << 4));
-                        const float wo = __shfl_sync(0xffffffffu, w_old, rr);
-                        v.x += old[i].x * wo; v.y += old[i].y * wo;
-                        v.z += old[i].z * wo; v.w += old[i].w * wo;
-                        if (warp_row0 + rr < p.Nq)
-                            *reinterpret_cast<float4*>(gbase + (size_t)rr * D + ch * 4) = v;
-                    }
-                    __syncwarp();   // the slice is rewritten by this warp's next tile
-                    if (row_ok && h == 0) {
-                        p.ml[grow * 2 + 0] = m_out;
-                        p.ml[grow * 2 + 1] = l_out;
-                    }
-                }
-                // O_t / S_t are free again: the next item's first P arrival orders after these reads
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_o_staged + 8 * ((it & 1u) * 2 + t));
-            }
-        }
-        } else {
         // =============================== softmax / correction / epilogue ===============================
         const int t = warp >> 2;                               // which Q tile of the pair
         const int row_in_tile = (warp & 3) * 32 + lane;        // TMEM lane == S/O row
@@ -1701,7 +1372,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
 #endif
         }
-        }   // one row per thread
     }
 
     // ---- teardown ----

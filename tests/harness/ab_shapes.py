@@ -19,8 +19,6 @@ for a in libs_arg:
     L.flash_attn_fwd.restype = ctypes.c_int
     if hasattr(L, "flash_attn_debug_set_split"):
         L.flash_attn_debug_set_split.argtypes = [ctypes.c_int]
-    if hasattr(L, "flash_attn_debug_set_coop"):
-        L.flash_attn_debug_set_coop.argtypes = [ctypes.c_int]
     libs.append((os.path.basename(path) + ("@" + tag if tag else ""), L, tag))
 shapes = [tuple(int(x) for x in s.split(",")) for s in shapes_arg]
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -37,8 +35,6 @@ for (B, H, N, D, causal) in shapes:
         for name, L, tag in libs:
             if tag.startswith("SPLIT") and hasattr(L, "flash_attn_debug_set_split"):
                 L.flash_attn_debug_set_split(int(tag.split("=")[1]))      # @SPLIT=0 pair items, @SPLIT=1 split mode, @SPLIT=-1 automatic
-            if tag.startswith("COOP") and hasattr(L, "flash_attn_debug_set_coop"):
-                L.flash_attn_debug_set_coop(int(tag.split("=")[1]))       # @COOP=0 one row per thread, @COOP=1 cooperative softmax
             for _ in range(3):
                 assert L.flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, D, causal, st) == 0
             torch.cuda.synchronize()

@@ -42,15 +42,3 @@ for t in range(2):
 c, ns, n = buf[20], buf[21], buf[22]
 if n:
     print(f"  CTA lifetime: {c / n:.0f} cycles = {ns / n / 1e3:.1f} us -> SM clock {c / ns * 1e3:.0f} MHz; kernel {ms * 1e3:.1f} us")
-
-nt = max(1, buf[2])   # sampled tiles of set 0 ~ probe samples are 1 in 8 of warp 0's tiles
-names = ["ld chunk a", "max a + exp a", "wait b + max b + post", "exp b", "collect + vote", "st P + publish", "-", "-", "-", "-"]
-tot = sum(buf[32 + i] for i in range(10))
-if tot:
-    calls = max(1, buf[32 + 10]) if buf[32 + 10] else None
-    print("  cooperative softmax phases (thread 0, share of the probed time): " + ", ".join(f"{n} {100.0 * buf[32 + i] / tot:.1f}%" for i, n in enumerate(names) if n != "-"))
-mn = ["QK: wait K", "QK: wait s_free", "QK: issue+commit", "PV: wait V", "PV: wait o_free", "PV: wait P h0", "PV: issue h0",
-      "PV: wait P h1", "PV: issue h1", "PV: commit"]
-npv = buf[48 + 10]
-if npv:
-    print("  MMA warp cycles per PV tile (all CTAs): " + ", ".join(f"{n} {buf[48 + i] / npv:.0f}" for i, n in enumerate(mn)))

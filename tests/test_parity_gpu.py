@@ -140,58 +140,6 @@ def test_pair_items_and_split_mode_both_match_the_oracle(fa, split, B, H, N, D, 
     gate(out, _oracle.attention(q, k, v, causal), f"split={split} B{B} H{H} N{N} D{D} causal={causal}")
 
 
-@pytest.mark.parametrize("coop", [False, True])
-@pytest.mark.parametrize("B,H,N,D,causal", [(1, 2, 1, 128, 1), (1, 3, 127, 128, 0), (2, 2, 129, 64, 1), (1, 4, 300, 128, 1),
-                                            (1, 2, 640, 128, 0), (2, 1, 1000, 64, 0), (1, 2, 1536, 128, 1), (1, 1, 2049, 128, 1),
-                                            (1, 2, 4224, 128, 1), (1, 1, 4096, 128, 0)])
-def test_both_softmax_forms_match_the_oracle(fa, coop, B, H, N, D, causal):
-    """One row per thread, and the cooperative form (the two softmax warps of a lane quadrant share every S tile and a
-    row's reference max; fa_fwd_sm100.cuh: coop_softmax_tile), both on pair items."""
-    q, k, v = normal((B, H, N, D), 23 + N)
-    fa.set_split(False)
-    fa.set_coop(coop)
-    try:
-        out = gpu_attention(fa, q, k, v, causal)
-    finally:
-        fa.set_split(None)
-        fa.set_coop(None)
-    if N <= 2049:
-        gate(out, _oracle.attention(q, k, v, causal), f"coop={coop} B{B} H{H} N{N} D{D} causal={causal}")
-    else:
-        rng = np.random.default_rng(N)
-        rows = np.unique(np.concatenate([np.arange(0, 130), np.arange(N - 130, N), rng.integers(0, N, 200)])).astype(np.int32)
-        bhs = np.repeat(np.arange(B * H, dtype=np.int32), len(rows))
-        rr = np.tile(rows, B * H)
-        ref = _oracle.attention_rows(q, k, v, causal, bhs, rr)
-        got = out.reshape(B * H, N, D)[bhs, rr]
-        gate(got, ref, f"coop={coop} N{N} causal={causal} (row-sampled)")
-
-
-@pytest.mark.parametrize("D,step_at,jump", [(128, 64, 12.0), (128, 0, 12.0), (64, 64, 20.0), (128, 96, 30.0), (128, 32, 7.0),
-                                            (128, 100, 7.0), (64, 0, 7.0), (128, 64, 4.0), (128, 40, 11.0), (128, 127, 10.3)])
-def test_cooperative_softmax_with_score_steps(fa, D, step_at, jump):
-    """The score-step inputs of test_score_steps_at_half_tile_boundaries against the cooperative form: steps land in either
-    warp's column half, below the lazy threshold (2^8), between the two, and past the hard one (2^15: both warps of a
-    quadrant rescale their halves of O and redo the tile)."""
-    N = 1024
-    rng = np.random.default_rng(3)
-    level = jump * np.floor((np.arange(N) + (128 - step_at)) / 128.0)
-    q = np.ones((1, 2, N, D), np.float32)
-    q[:, 1] *= 0.5
-    k = np.broadcast_to((level / np.sqrt(D))[None, None, :, None], (1, 2, N, D)).astype(np.float32)
-    k = k + rng.standard_normal((1, 2, N, D), dtype=np.float32) * 0.02
-    v = rng.standard_normal((1, 2, N, D), dtype=np.float32) * 0.5
-    q, k, v = q.astype(np.float16), k.astype(np.float16), v.astype(np.float16)
-    fa.set_split(False)
-    fa.set_coop(True)
-    try:
-        for causal in (0, 1):
-            gate(gpu_attention(fa, q, k, v, causal), _oracle.attention(q, k, v, causal), f"D{D} step@{step_at} causal={causal}")
-    finally:
-        fa.set_split(None)
-        fa.set_coop(None)
-
-
 def test_split_mode_merges_slots_whose_references_differ(fa):
     """Even KV tiles hold small scores, odd ones large (and vice versa): the two slots end with very different reference
     maxima and the merge weights w = exp(m_s - max m) do the work."""
