@@ -22,9 +22,9 @@ the north-star target length).  Prints ONE JSON line (rank 0):
 Under torchrun (N > 1) the line additionally carries, measured in the same process group:
   strong_cfg3   BASELINE config 3 (B16 H32 N8192 causal) with its 512 heads split over the ranks, no collective
                 (reference flash_attention.cu:120-122: heads are independent)
-  cp_cfg5       BASELINE config 5 (B1 H32 N131072 causal) context-parallel over the ranks, `pull` (copy-engine
-                reads of the peers' K/V) and `sendrecv` (NCCL ring), next to the no-communication bound
-                (the same shape with its heads split)
+  cp_cfg5       BASELINE config 5 (B1 H32 N131072 causal) context-parallel over the ranks: `gather` (copy-engine pulls
+                into one gathered K/V buffer, two kernels per rank), `pull` (the same pulls, partial states + merge)
+                and `sendrecv` (NCCL ring), next to the no-communication bound (the same shape with its heads split)
   cp_parity     context-parallel output rows of every rank against the CPU oracle (gate 2e-3 / 2e-4;
                 the process exits non-zero when it fails)
 
@@ -215,8 +215,9 @@ def cp_setup(workload, rank, world, local_rank, exchange):
     C = N // (2 * world)
     mine = ring.zigzag_chunks(rank, world)
     q = [cp_chunk(0, c, B, H, C, D) for c in mine]
-    if exchange == "pull":
-        px = ring.peer_kv(B, H, C, D, torch.device("cuda", local_rank))
+    if exchange in ("pull", "gather"):
+        # K/V are produced straight into the peer-readable block (pull) / the rank's own slots of its gathered buffer
+        px = (ring.peer_kv if exchange == "pull" else ring.gathered_kv)(B, H, C, D, torch.device("cuda", local_rank))
         for slot, c in enumerate(mine):
             px.k[slot].copy_(cp_chunk(1, c, B, H, C, D))
             px.v[slot].copy_(cp_chunk(2, c, B, H, C, D))
@@ -332,7 +333,9 @@ def bench_ring(args, workload, rank, world, local_rank, barrier, max_over_ranks)
                        "parallelism": (f"cp{world} zig-zag, "
                                        + ("copy-engine pulls of the unmasked K/V chunks from the owner's HBM "
                                           "(flash_attn_peer_copy), no communication kernel"
-                                          if args.ring_exchange == "pull" else "NCCL send/recv of K/V chunk pairs")
+                                          if args.ring_exchange == "pull" else
+                                          "copy-engine pulls into one gathered K/V buffer, two kernels per rank, no partial states"
+                                          if args.ring_exchange == "gather" else "NCCL send/recv of K/V chunk pairs")
                                        + f" (<= {4 * B * H * C * D * 2 / 2**20:.0f} MiB per hop per rank)") if world > 1
                        else "single GPU, monolithic kernel"},
             "roofline": {"bound": "tensor", "achieved": round(fl / (ms * 1e-3) / 1e12 / world, 2),
@@ -351,7 +354,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
-    ap.add_argument("--ring-exchange", default="pull", choices=["pull", "sendrecv"],
+    ap.add_argument("--ring-exchange", default="gather", choices=["gather", "pull", "sendrecv"],
                     help="cfg5 only: how the ranks get at each other's K/V (flash_attention_cuda_b200/ring.py)")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--sweep", action="store_true", help="also print the README-style TFLOPS table to stderr")
@@ -614,15 +617,21 @@ def main():
               "heads_split_bound": {"ms": round(ms5_heads, 3), "tflops": round(fl5 / (ms5_heads * 1e-3) / 1e12, 1),
                                     "heads_per_rank": cnt5}}
         outs = {}
-        for ex in ("pull", "sendrecv"):
+        for ex in ("gather", "pull", "sendrecv"):
             ms5, out = cp_time(w5, rank, world, local_rank, ex, 4, 3, barrier, max_over_ranks)
             outs[ex] = [t.clone() for t in out]
+            del out
+            if ex != "sendrecv":
+                ring.release_peer_kv()         # one peer-readable K/V set at a time
+                torch.cuda.empty_cache()
             cp[ex] = {"ms": round(ms5, 3), "tflops": round(fl5 / (ms5 * 1e-3) / 1e12, 1),
                       "efficiency": round(ms5_heads / ms5, 4),
                       "frac_of_sustained_peak_per_gpu": round(fl5 / (ms5 * 1e-3) / 1e12 / world / pk0["tflops_sustained"], 4)
                       if pk0["tflops_sustained"] else None}
         cp["note"] = ("efficiency = heads-split time (same shape, no communication, measured in this run) / context-parallel "
-                      "time; pull = copy-engine reads of the owners' K/V chunks over NVLink, sendrecv = NCCL ring")
+                      "time; gather = copy-engine pulls into one gathered K/V buffer per head, two kernels per rank, no partial "
+                      "states; pull = the same pulls, one kernel and one partial state per chunk pair, merged at the end; "
+                      "sendrecv = NCCL ring with those kernels")
         multi["cp_cfg5"] = cp
         par = cp_parity(w5, rank, world, outs)
         if rank == 0:

@@ -37,6 +37,8 @@ EXPORTED_SYMBOLS = (
     "flash_attn_fwd",
     "flash_attn_fwd_bf16",
     "flash_attn_fwd_ex",
+    "flash_attn_fwd_gathered",
+    "flash_attn_stream_write_flag",
     "flash_attn_finalize",
     "flash_attn_merge",
     "flash_attn_fwd_host",
@@ -47,6 +49,7 @@ EXPORTED_SYMBOLS = (
     "flash_attn_peer_close",
     "flash_attn_peer_free",
     "flash_attn_peer_copy",
+    "flash_attn_peer_copy_2d",
     "flash_attn_status",
     "flash_attn_launch_count",
     "flash_attn_destroy",
@@ -101,6 +104,13 @@ def lib() -> ctypes.CDLL:
         L.flash_attn_fwd_bf16.restype = ci
     L.flash_attn_fwd_ex.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ll, ll, ci, vp]
     L.flash_attn_fwd_ex.restype = ci
+    if hasattr(L, "flash_attn_fwd_gathered"):   # absent from archived A/B builds of older kernels
+        L.flash_attn_fwd_gathered.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ll, ll, vp, ci, vp]
+        L.flash_attn_fwd_gathered.restype = ci
+        L.flash_attn_stream_write_flag.argtypes = [vp, ci, vp]
+        L.flash_attn_stream_write_flag.restype = ci
+        L.flash_attn_peer_copy_2d.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp]
+        L.flash_attn_peer_copy_2d.restype = ci
     L.flash_attn_finalize.argtypes = [vp, vp, vp, ll, ci, vp]
     L.flash_attn_finalize.restype = ci
     if hasattr(L, "flash_attn_merge"):   # absent from archived A/B builds of older kernels
@@ -233,6 +243,27 @@ def flash_attn_fwd_partial(q, k, v, o_partial, ml, causal: bool, q_offset: int, 
     check(rc)
 
 
+def flash_attn_fwd_gathered(q, k_ptr: int, v_ptr: int, out, Nkv: int, kv_head_rows: int, causal: bool, q_offset: int,
+                            ready=None, ready_rows: int = 0, stream=None):
+    """Attention of q [B, H, Nq, D] (FP16, at global positions q_offset..) against a GATHERED K/V buffer: raw device pointers
+    to B*H heads of `kv_head_rows` rows each, the first Nkv in use (include/flash_attn.h).  `ready`: optional int32 CUDA
+    tensor of per-chunk flags (one per `ready_rows` rows) the kernel waits on while copies are still landing."""
+    import torch
+    if not q.is_cuda or q.dtype != torch.float16 or q.dim() != 4 or not q.is_contiguous():
+        raise TypeError("q must be a contiguous float16 CUDA tensor [B, H, Nq, D]")
+    if out.shape != q.shape or out.dtype != q.dtype or out.device != q.device or not out.is_contiguous():
+        raise ValueError("out must match q")
+    if ready is not None and (ready.dtype != torch.int32 or ready.device != q.device or not ready.is_contiguous()):
+        raise TypeError("ready must be a contiguous int32 tensor on the device of q")
+    B, H, Nq, D = q.shape
+    with torch.cuda.device(q.device):
+        rc = lib().flash_attn_fwd_gathered(q.data_ptr(), k_ptr, v_ptr, out.data_ptr(), B, H, Nq, Nkv, D, 1 if causal else 0,
+                                           q_offset, kv_head_rows, ready.data_ptr() if ready is not None else None,
+                                           ready_rows, _stream_ptr(stream))
+    check(rc)
+    return out
+
+
 def _check_f16_out(out, rows, D, name="out"):
     import torch
     if not out.is_cuda or out.dtype != torch.float16 or not out.is_contiguous():
@@ -337,6 +368,16 @@ def peer_free(ptr: int) -> None:
 def peer_copy(dst_ptr: int, src_ptr: int, nbytes: int, stream=None) -> None:
     """Enqueue a copy-engine transfer (any mix of local and mapped peer pointers) on a torch stream."""
     check(lib().flash_attn_peer_copy(dst_ptr, src_ptr, nbytes, _stream_ptr(stream)))
+
+
+def peer_copy_2d(dst_ptr: int, dpitch: int, src_ptr: int, spitch: int, width: int, height: int, stream=None) -> None:
+    """`height` rows of `width` bytes, pitches in bytes (copy engine; local and mapped peer pointers alike)."""
+    check(lib().flash_attn_peer_copy_2d(dst_ptr, dpitch, src_ptr, spitch, width, height, _stream_ptr(stream)))
+
+
+def stream_write_flag(flag_ptr: int, value: int, stream=None) -> None:
+    """*flag = value, ordered behind the work already queued on the stream; a stream memory operation, no kernel."""
+    check(lib().flash_attn_stream_write_flag(flag_ptr, value, _stream_ptr(stream)))
 
 
 def launch_count() -> int:

@@ -47,6 +47,7 @@ constexpr int kTmapCache = 8;        // cached descriptor sets per device (flash
 struct TmapSet {
     const void *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr;
     int BH = 0, Nq = 0, Nkv = 0, D = 0, bf16 = 0;
+    long long kv_head_rows = 0;
     unsigned long long stamp = 0;    // 0 = empty; otherwise the LRU clock of its last use
     CUtensorMap tq, tk, tv, to;
 };
@@ -163,11 +164,13 @@ int take_watchdog(DeviceState* st) {
 
 // [BH, N, D] fp16, box = 64 halves x `rows` rows x 1 head, 128-byte swizzle; rows past N read as zero
 // (and are dropped on a TMA store).
-int make_tmap(CUtensorMap* tm, const void* base, int BH, int N, int D, int rows = fa::kBlockN, bool bf16 = false) {
+int make_tmap(CUtensorMap* tm, const void* base, int BH, int N, int D, int rows = fa::kBlockN, bool bf16 = false,
+              long long head_rows = 0) {
     std::call_once(g_encode_once, load_encode_fn);
     if (!g_encode) return FA_ERR_TENSORMAP;
+    if (head_rows < N) head_rows = N;         // rows between two heads (gathered K/V: the buffer holds more rows than are used)
     cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)BH};
-    cuuint64_t gstride[2] = {(cuuint64_t)D * 2, (cuuint64_t)N * D * 2};
+    cuuint64_t gstride[2] = {(cuuint64_t)D * 2, (cuuint64_t)head_rows * D * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -277,12 +280,12 @@ int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const 
 // were seen before: cuTensorMapEncodeTiled x 4 is most of the host time of a launch, and short sequences
 // (BASELINE config 1: ~20 us of GPU time) are called in loops on the same buffers.
 int get_tmaps(DeviceState* st, const void* q, const void* k, const void* v, const void* o, const fa::Params& p, int D,
-              bool bf16, TmapSet* out) {
+              bool bf16, TmapSet* out, long long kv_head_rows = 0) {
     {
         std::lock_guard<std::mutex> lock(st->tmap_mu);
         for (TmapSet& c : st->tmaps)
             if (c.stamp && c.q == q && c.k == k && c.v == v && c.o == o && c.BH == p.BH && c.Nq == p.Nq && c.Nkv == p.Nkv &&
-                c.D == D && c.bf16 == (int)bf16) {
+                c.D == D && c.bf16 == (int)bf16 && c.kv_head_rows == kv_head_rows) {
                 c.stamp = ++st->tmap_clock;
                 *out = c;
                 return FA_OK;
@@ -291,10 +294,11 @@ int get_tmaps(DeviceState* st, const void* q, const void* k, const void* v, cons
     TmapSet t;
     t.q = q; t.k = k; t.v = v; t.o = o;
     t.BH = p.BH; t.Nq = p.Nq; t.Nkv = p.Nkv; t.D = D; t.bf16 = (int)bf16;
+    t.kv_head_rows = kv_head_rows;
     int rc;
     if ((rc = make_tmap(&t.tq, q, p.BH, p.Nq, D, fa::kBlockN, bf16)) != FA_OK) return rc;
-    if ((rc = make_tmap(&t.tk, k, p.BH, p.Nkv, D, fa::kBlockN, bf16)) != FA_OK) return rc;
-    if ((rc = make_tmap(&t.tv, v, p.BH, p.Nkv, D, fa::kBlockN, bf16)) != FA_OK) return rc;
+    if ((rc = make_tmap(&t.tk, k, p.BH, p.Nkv, D, fa::kBlockN, bf16, kv_head_rows)) != FA_OK) return rc;
+    if ((rc = make_tmap(&t.tv, v, p.BH, p.Nkv, D, fa::kBlockN, bf16, kv_head_rows)) != FA_OK) return rc;
     // O store map (unused in partial mode: describe Q's extent on a valid pointer)
     if ((rc = make_tmap(&t.to, o ? o : q, p.BH, p.Nq, D, fa::kBlockN, bf16)) != FA_OK) return rc;
     {
@@ -309,14 +313,15 @@ int get_tmaps(DeviceState* st, const void* q, const void* k, const void* v, cons
     return FA_OK;
 }
 
-int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaStream_t stream, bool bf16 = false) {
+int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaStream_t stream, bool bf16 = false,
+        long long kv_head_rows = 0) {
     int err = 0;
     DeviceState* st = device_state(&err);
     if (!st) return err;
     if ((err = take_watchdog(st)) != FA_OK) return err;
     if ((long long)p.BH * p.nqp > 0x7fffffffLL) return FA_ERR_BAD_SHAPE;
     TmapSet t;
-    int rc = get_tmaps(st, q, k, v, p.partial_mode ? nullptr : (const void*)p.o, p, D, bf16, &t);
+    int rc = get_tmaps(st, q, k, v, p.partial_mode ? nullptr : (const void*)p.o, p, D, bf16, &t, kv_head_rows);
     if (rc != FA_OK) return rc;
     const bool poly = use_poly(D, p.Nkv, p.causal);
     if (bf16) {
@@ -367,6 +372,46 @@ int flash_attn_fwd_ex(const void* q, const void* k, const void* v, float* o_part
     p.partial_mode = 1;
     p.accumulate = accumulate ? 1 : 0;
     return run(q, k, v, p, D, static_cast<cudaStream_t>(stream));
+}
+
+int flash_attn_fwd_gathered(const void* q, const void* k, const void* v, void* o, int B, int H, int Nq, int Nkv, int D,
+                            int causal, long long q_offset, long long kv_head_rows, const int* ready, int ready_rows,
+                            void* stream) {
+    int rc = validate(q, k, v, o, B, H, Nq, Nkv, D);
+    if (rc != FA_OK) return rc;
+    if (kv_head_rows < Nkv) return FA_ERR_BAD_SHAPE;
+    if (ready && (ready_rows < fa::kBlockN || ready_rows % fa::kBlockN != 0)) return FA_ERR_BAD_SHAPE;
+    fa::Params p = make_params(B * H, Nq, Nkv, D, causal, q_offset, /*split=*/false);
+    p.o = static_cast<__half*>(o);
+    p.ready = ready;
+    p.ready_rows = ready ? ready_rows : 0;
+    return run(q, k, v, p, D, static_cast<cudaStream_t>(stream), /*bf16=*/false, kv_head_rows);
+}
+
+typedef CUresult (*StreamWriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+int flash_attn_stream_write_flag(int* flag, int value, void* stream) {
+    if (!flag) return FA_ERR_NULL_PTR;
+    static StreamWriteValue32Fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<StreamWriteValue32Fn>(f);
+    }();
+    if (!fn) return FA_ERR_WORKSPACE;
+    // a stream memory operation: ordered behind the copies queued on `stream`, executed without a kernel (no SM is free
+    // next to the persistent attention grid)
+    return fn(static_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(flag), (cuuint32_t)value, 0) == CUDA_SUCCESS
+               ? FA_OK : (int)cudaErrorUnknown;
+}
+
+int flash_attn_peer_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                            void* stream) {
+    if (!dst || !src) return FA_ERR_NULL_PTR;
+    if (width == 0 || height == 0) return FA_OK;
+    if (width > dpitch || width > spitch) return FA_ERR_BAD_SHAPE;
+    return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault, (cudaStream_t)stream);
 }
 
 int flash_attn_finalize(const float* o_partial, const float* ml, void* o, long long rows, int D, void* stream) {

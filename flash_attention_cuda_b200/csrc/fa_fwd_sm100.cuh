@@ -144,6 +144,10 @@ struct Params {
     int accumulate;
     int zero;           // always 0: trip count of the empty loops that fence ptxas' instruction scheduler (FA_SCHED_FENCE)
     int* sched;         // {next work index, finished CTAs}: dynamic tile scheduler state, self-resetting
+    // Gathered K/V (context parallelism, flash_attn_fwd_gathered): K/V rows [i * ready_rows, (i + 1) * ready_rows) of every
+    // head may be loaded once ready[i] != 0 -- another stream's copy engine is still filling the buffer while the kernel runs
+    const int* ready;
+    int ready_rows;
     float scale;        // 1/sqrt(D)
     float scale_log2;   // scale * log2(e)
 };
@@ -826,6 +830,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (warp == kLoadWarp) {
         // =============================== TMA producer ===============================
         Ring ring{0u, 0u};
+        int ready_upto = 0;            // gathered K/V: chunks [0, ready_upto) are known to have landed
         for (uint32_t it = 0;; ++it) {
             // claim the next work item and publish it
             const uint32_t slot = it & 1u;
@@ -854,6 +859,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
             __syncwarp();
             auto load_kv = [&](const CUtensorMap* tm, int j) {
+                if (p.ready != nullptr) {
+                    // chunk of the gathered K/V this tile lies in: wait until its copy has landed.  Flags only ever turn
+                    // on during a launch, so what has been seen ready stays ready for the later items.
+                    const int chunk = (j * kBlockN) / p.ready_rows;
+                    if (chunk >= ready_upto) {
+                        const unsigned long long t0 = global_timer_ns();
+                        while (ld_acquire_sys(p.ready + chunk) == 0) {
+                            __nanosleep(200);
+                            if (watchdog_aborted()) break;
+                            if (global_timer_ns() - t0 > kWatchdogNs) { watchdog_raise(70); break; }
+                        }
+                        ready_upto = chunk + 1;
+                    }
+                }
                 const uint32_t full = bar_kv_full + 8 * ring.idx;
                 mbar_wait(bar_kv_empty + 8 * ring.idx, ring.phase ^ 1u, 2);
                 if (elect_one()) {

@@ -171,6 +171,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
         }
     }
 }
+// a flag another engine of the system (copy engine, stream memory op) sets while the kernel runs
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 // named barrier among `count` threads of the CTA (id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");

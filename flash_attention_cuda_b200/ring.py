@@ -12,6 +12,12 @@
       of hop h-1 run.  No communication kernel competes with the persistent attention grid for SMs, and
       the ranks are not chained to each other: two tiny all-reduces per step (everyone's K/V in place /
       everyone done reading) are the only collectives.
+    - exchange="gather" (causal; the fastest): the pulls land in ONE buffer per head that holds the rank's whole visible key
+      sequence -- chunks entirely in the past in arrival order, the rank's own high chunk (the diagonal) last -- and a
+      rank runs just two kernels, one per Q chunk, over that gathered sequence (`flash_attn_fwd_gathered`): the
+      accumulators stay in tensor memory across every hop, no partial state is written, nothing is merged.  The
+      kernels are launched at once; their TMA producer waits on per-chunk flags that the copy stream sets behind each
+      pull (`GatheredKV`).
     - exchange="sendrecv": K/V chunk pairs rotate with NCCL send/recv on a side stream (also the path
       the gloo CPU test runs); needs `flash_attn_set_sm_margin` so that NCCL's kernel finds a free SM.
   Per-hop math is `flash_attn_fwd_ex`: every chunk
@@ -197,10 +203,164 @@ def peer_kv(B: int, H: int, C: int, D: int, device, group=None) -> PeerKV:
 
 
 def release_peer_kv() -> None:
-    """Collective: drop the cached PeerKV (call before destroying the process group)."""
+    """Collective: drop the cached PeerKV / GatheredKV (call before destroying the process group)."""
     for px in _peer_kv.values():
         px.close()
     _peer_kv.clear()
+    for gk in _gathered_kv.values():
+        gk.close()
+    _gathered_kv.clear()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# exchange="gather": the rank's visible keys in one buffer, two kernels, no partial states
+# ---------------------------------------------------------------------------------------------------------------------
+def gather_layout(rank: int, world: int) -> List[Tuple[int, int]]:
+    """Slots of rank `rank`'s gathered K/V buffer under a causal mask, as (owner rank, 0 = its low chunk / 1 = its high
+    chunk).  Order = order of arrival with the staggered schedule (hop h pulls from rank r - h, so at every hop the P ranks
+    read from P distinct owners), own chunks where the mask needs them:
+        low chunks of ranks r-1, ..., 0      entirely in the past of both Q chunks          (hops 1 .. r)
+        own low chunk                         diagonal of the low Q chunk, in the past of the high one
+        low + high chunk of ranks P-1 .. r+1  in the past of the high Q chunk only           (hops r+1 .. P-1)
+        own high chunk                        diagonal of the high Q chunk
+    The low Q chunk attends to the first r + 1 slots, the high one to all 2P - r; in both cases every slot but the last is
+    entirely visible, so the kernel's single causal offset describes the mask although the keys are not in sequence order."""
+    lay = [(s, 0) for s in range(rank - 1, -1, -1)] + [(rank, 0)]
+    for s in range(world - 1, rank, -1):
+        lay += [(s, 0), (s, 1)]
+    return lay + [(rank, 1)]
+
+
+def gather_slot(buffer_rank: int, world: int, owner: int, which: int) -> int:
+    """Slot of chunk (owner, which) in the gathered buffer of rank `buffer_rank`."""
+    return gather_layout(buffer_rank, world).index((owner, which))
+
+
+class GatheredKV:
+    """Peer-readable gathered K/V of one rank: [K | V], each B*H heads of nslots*C rows, slot order = gather_layout.
+    The rank's own chunks live in slots r and nslots-1 (`self.k` / `self.v` are strided views of them: a caller that produces
+    K/V there pays no staging copy); the other ranks read them from there.  Collective constructor."""
+
+    def __init__(self, B: int, H: int, C: int, D: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import peer_alloc, peer_open
+        self.group, self.dev = group, torch.device(device)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.B, self.H, self.C, self.D = B, H, C, D
+        self.layout = gather_layout(self.rank, self.world)
+        self.nslots = len(self.layout)
+        self.chunk_row_bytes = C * D * 2                         # one head of one chunk
+        self.head_bytes = self.nslots * self.chunk_row_bytes     # one head of the gathered sequence
+        self.tensor_bytes = B * H * self.head_bytes              # K (or V) region
+        self.block, handle, self.ptr = peer_alloc(2 * self.tensor_bytes, self.dev)
+        kv = self.block.view(torch.float16).view(2, B, H, self.nslots, C, D)
+        own = (self.rank, self.nslots - 1)
+        self.k = [kv[0, :, :, s] for s in own]                   # [B, H, C, D] views, head stride nslots*C*D
+        self.v = [kv[1, :, :, s] for s in own]
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        self.peer_ptr = [self.ptr if r == self.rank else peer_open(handles[r]) for r in range(self.world)]
+        self.flags = torch.zeros(self.nslots, dtype=torch.int32, device=self.dev)
+        self.sync = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.comm = torch.cuda.Stream(device=self.dev)
+
+    @property
+    def k_ptr(self) -> int:
+        return self.ptr
+
+    @property
+    def v_ptr(self) -> int:
+        return self.ptr + self.tensor_bytes
+
+    def begin(self, k, v):
+        """Own chunks into their slots (unless the caller wrote them there), flags reset, 'every block is in place', then
+        the pulls of all hops are queued on the copy stream, each followed by its chunks' ready flags."""
+        import torch
+        import torch.distributed as dist
+        from . import peer_copy_2d, stream_write_flag
+        cur = torch.cuda.current_stream(self.dev)
+        for mine, given in zip(self.k + self.v, list(k) + list(v)):
+            if mine.data_ptr() != given.data_ptr():
+                mine.copy_(given)
+        self.flags.zero_()
+        self.flags[self.rank] = 1
+        self.flags[self.nslots - 1] = 1
+        dist.all_reduce(self.sync, group=self.group)             # stream-ordered behind the copies above
+        self.comm.wait_stream(cur)
+        P, r = self.world, self.rank
+        heads = self.B * self.H
+        for hop in range(1, P):
+            src = (r - hop) % P
+            src_head_bytes = (2 * P - src) * self.chunk_row_bytes
+            src_tensor_bytes = heads * src_head_bytes
+            for which in ((0,) if src < r else (0, 1)):           # an owner behind us contributes only its low chunk
+                dst_slot = self.layout.index((src, which))
+                src_slot = src if which == 0 else 2 * P - src - 1
+                for t in range(2):                                 # K region, V region
+                    peer_copy_2d(self.ptr + t * self.tensor_bytes + dst_slot * self.chunk_row_bytes, self.head_bytes,
+                                 self.peer_ptr[src] + t * src_tensor_bytes + src_slot * self.chunk_row_bytes, src_head_bytes,
+                                 self.chunk_row_bytes, heads, self.comm)
+                stream_write_flag(self.flags.data_ptr() + 4 * dst_slot, 1, self.comm)
+
+    def end(self):
+        """Everyone is done reading everyone's block: K/V may be rewritten after this (stream-ordered)."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.current_stream(self.dev).wait_stream(self.comm)
+        dist.all_reduce(self.sync, group=self.group)
+
+    def close(self):
+        import torch
+        import torch.distributed as dist
+        from . import peer_close, peer_free
+        torch.cuda.synchronize(self.dev)
+        for r, ptr in enumerate(self.peer_ptr):
+            if r != self.rank:
+                peer_close(ptr)
+        dist.barrier(group=self.group)
+        self.k = self.v = self.block = None
+        peer_free(self.ptr)
+
+
+_gathered_kv: dict = {}
+
+
+def gathered_kv(B: int, H: int, C: int, D: int, device, group=None) -> GatheredKV:
+    """The cached GatheredKV for this shape (collective on first use; one shape at a time)."""
+    import torch
+    key = (str(torch.device(device)), B, H, C, D, id(group))
+    gk = _gathered_kv.get(key)
+    if gk is None:
+        for old in _gathered_kv.values():
+            old.close()
+        _gathered_kv.clear()
+        gk = _gathered_kv[key] = GatheredKV(B, H, C, D, device, group)
+    return gk
+
+
+def gather_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, group=None, *, gathered=None):
+    """Context-parallel forward over a gathered K/V buffer (module docstring); causal only.  Same arguments and result as
+    `ring_attention_forward`; k / v may be the views `gathered_kv(...).k / .v` themselves."""
+    import torch
+    from . import flash_attn_fwd_gathered
+    if not causal:
+        raise ValueError("exchange='gather' serves the causal mask (every chunk is either entirely visible or the diagonal); "
+                         "use exchange='pull' without one")
+    B, H, C, D = q[0].shape
+    for t in q:
+        if t.dtype != torch.float16 or not t.is_contiguous() or t.shape != q[0].shape:
+            raise TypeError("q chunks must be contiguous float16 [B, H, C, D] tensors of one shape")
+    gk = gathered or gathered_kv(B, H, C, D, q[0].device, group)
+    gk.begin(k, v)
+    n = gk.nslots
+    out = [torch.empty_like(q[0]), torch.empty_like(q[1])]
+    # the low Q chunk first: it needs the slots that land first (the low chunks of the ranks behind us), so the pulls of the
+    # later hops run under it; the high chunk's launch then finds most of its slots in place
+    flash_attn_fwd_gathered(q[0], gk.k_ptr, gk.v_ptr, out[0], (gk.rank + 1) * C, n * C, True, gk.rank * C, gk.flags, C)
+    flash_attn_fwd_gathered(q[1], gk.k_ptr, gk.v_ptr, out[1], n * C, n * C, True, (n - 1) * C, gk.flags, C)
+    gk.end()
+    return out
 
 
 def _check_chunks(q, k, v):
@@ -303,13 +463,15 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
     import torch
     import torch.distributed as dist
 
-    _check_chunks(q, k, v)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    if exchange == "gather":               # K/V may be the strided views of the gathered buffer itself
+        return gather_attention_forward(q, k, v, causal, group)
+    _check_chunks(q, k, v)
     if exchange is None:
         exchange = os.environ.get("FLASH_ATTN_RING_EXCHANGE") or ("pull" if q[0].is_cuda and world > 1 else "sendrecv")
     if exchange not in ("pull", "sendrecv"):
-        raise ValueError(f"exchange must be 'pull' or 'sendrecv', not {exchange!r}")
+        raise ValueError(f"exchange must be 'pull', 'gather' or 'sendrecv', not {exchange!r}")
     if exchange == "pull":
         return pull_attention_forward(q, k, v, causal, group, partial=partial, finalize=finalize)
     partial = partial or _cuda_partial

@@ -61,6 +61,21 @@ int flash_attn_fwd_ex(const void* q, const void* k, const void* v, float* o_part
                       long long kv_offset, int accumulate, void* stream);
 int flash_attn_finalize(const float* o_partial, const float* ml, void* o, long long rows, int D,
                         void* stream);
+
+/* Context parallelism without partial states (the reference has no multi-GPU code; its split-K partials, FA.cu:460-496,
+ * are what the entry above serves).  The queries q[B,H,Nq,D] sit at global positions q_offset.. of a sequence whose visible
+ * keys have been GATHERED into one buffer per head: k, v point at B*H heads of `kv_head_rows` rows each, of which the first
+ * Nkv are used; key row c is visible to query row r iff c <= r + q_offset (causal) -- keys entirely in the past may stand in
+ * any order, the chunk that contains the diagonal comes last.  O[B,H,Nq,D] is written as FP16 like flash_attn_fwd: the
+ * accumulators stay in tensor memory across the whole gathered sequence, nothing is merged afterwards.
+ * `ready` (optional): int flags, one per `ready_rows` rows of the gathered sequence (a multiple of 128).  The kernel loads
+ * rows [i*ready_rows, (i+1)*ready_rows) only after ready[i] != 0, so it may be launched while copy engines are still
+ * filling the buffer (flash_attn_peer_copy_2d + flash_attn_stream_write_flag on another stream). */
+int flash_attn_fwd_gathered(const void* q, const void* k, const void* v, void* o, int B, int H, int Nq, int Nkv, int D,
+                            int causal, long long q_offset, long long kv_head_rows, const int* ready, int ready_rows,
+                            void* stream);
+/* *flag = value as a stream memory operation (cuStreamWriteValue32): ordered behind the work queued on `stream`, needs no SM. */
+int flash_attn_stream_write_flag(int* flag, int value, void* stream);
 /* The reference's flash_attention_splitk_merge (FA.cu:559-598; defined there, never launched): merges
  * `splits` independent partial states, o_partial [splits][rows][D] and ml [splits][rows][2] (each written
  * by a flash_attn_fwd_ex call with accumulate = 0), into FP16 O = sum_s w_s O_s / sum_s w_s l_s,
@@ -113,6 +128,10 @@ int flash_attn_peer_open(const unsigned char* handle, void** ptr);
 int flash_attn_peer_close(void* ptr);
 int flash_attn_peer_free(void* ptr);
 int flash_attn_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+/* the same for `height` rows of `width` bytes with different pitches on either side (a [heads][rows][D] chunk into / out of a
+ * buffer that holds more rows per head) */
+int flash_attn_peer_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                            void* stream);
 
 /* Kernel watchdog.  Every barrier wait inside the kernel gives up after 10 s (a protocol bug, or a device so
  * oversubscribed that a CTA did not run for that long): the kernel then drains, its output is garbage, and a record

@@ -25,8 +25,8 @@ g = torch.Generator(device="cuda").manual_seed(99)          # identical global t
 q, k = (torch.randn((B, H, N, D), device="cuda", generator=g).half() for _ in range(2))
 v = (torch.randn((B, H, N, D), device="cuda", generator=g) * 0.5).half()
 ok = True
-EXCHANGES = sys.argv[2].split(",") if len(sys.argv) > 2 else ["pull", "sendrecv"]
-for causal, exchange in [(c, e) for e in EXCHANGES for c in (True, False)]:
+EXCHANGES = sys.argv[2].split(",") if len(sys.argv) > 2 else ["pull", "sendrecv", "gather"]
+for causal, exchange in [(c, e) for e in EXCHANGES for c in (True, False) if c or e != "gather"]:   # gather: causal only
     full = fa.flash_attn_fwd(q, k, v, causal=causal)
     C = N // (2 * world)
     lo, hi = ring.zigzag_chunks(rank, world)

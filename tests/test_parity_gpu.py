@@ -140,6 +140,71 @@ def test_pair_items_and_split_mode_both_match_the_oracle(fa, split, B, H, N, D, 
     gate(out, _oracle.attention(q, k, v, causal), f"split={split} B{B} H{H} N{N} D{D} causal={causal}")
 
 
+def test_gathered_kv_entry_matches_the_oracle_with_permuted_past_chunks(fa):
+    """flash_attn_fwd_gathered on one GPU: the keys of a causal problem cut into chunks, the chunks in the past of the queries
+    stored in a scrambled order in a buffer with room for more rows per head, the diagonal chunk last, per-chunk ready flags
+    set beforehand -- the result for the last chunk's queries must be that of the plain causal problem."""
+    B, H, C, D, nch = 1, 3, 256, 128, 5
+    N = nch * C
+    q, k, v = normal((B, H, N, D), 77)
+    ref = _oracle.attention(q, k, v, 1)[:, :, (nch - 1) * C:]
+    order = [2, 0, 3, 1, 4]                                   # past chunks in any order, the diagonal one last
+    slots = nch + 2                                           # the buffer holds more rows per head than are used
+    kb = torch.full((B * H, slots * C, D), float("nan"), dtype=torch.float16, device="cuda")
+    vb = torch.full_like(kb, float("nan"))
+    tk, tv = torch.from_numpy(k).cuda().view(B * H, N, D), torch.from_numpy(v).cuda().view(B * H, N, D)
+    for s, c in enumerate(order):
+        kb[:, s * C:(s + 1) * C] = tk[:, c * C:(c + 1) * C]
+        vb[:, s * C:(s + 1) * C] = tv[:, c * C:(c + 1) * C]
+    tq = torch.from_numpy(np.ascontiguousarray(q[:, :, (nch - 1) * C:])).cuda()
+    out = torch.empty_like(tq)
+    ready = torch.ones(nch, dtype=torch.int32, device="cuda")
+    fa.flash_attn_fwd_gathered(tq, kb.data_ptr(), vb.data_ptr(), out, nch * C, slots * C, True, (nch - 1) * C, ready, C)
+    torch.cuda.synchronize()
+    assert not fa.watchdog_status()["aborted"]
+    gate(out.cpu().numpy(), ref, "gathered, flags preset")
+    # the same without flags, and a middle Q chunk: only a prefix of the gathered sequence is visible to it
+    order2 = [1, 0, 2]
+    for s, c in enumerate(order2):
+        kb[:, s * C:(s + 1) * C] = tk[:, c * C:(c + 1) * C]
+        vb[:, s * C:(s + 1) * C] = tv[:, c * C:(c + 1) * C]
+    tq2 = torch.from_numpy(np.ascontiguousarray(q[:, :, 2 * C:3 * C])).cuda()
+    out2 = torch.empty_like(tq2)
+    fa.flash_attn_fwd_gathered(tq2, kb.data_ptr(), vb.data_ptr(), out2, 3 * C, slots * C, True, 2 * C)
+    torch.cuda.synchronize()
+    gate(out2.cpu().numpy(), _oracle.attention(q, k, v, 1)[:, :, 2 * C:3 * C], "gathered, middle chunk")
+
+
+def test_gathered_kv_kernel_waits_for_chunks_that_land_later(fa):
+    """The kernel is launched first and the ready flags are raised afterwards from another stream (stream memory
+    operations behind the copies that fill the buffer), as the context-parallel driver does."""
+    B, H, C, D, nch = 1, 2, 512, 128, 4
+    N = nch * C
+    q, k, v = normal((B, H, N, D), 78)
+    tk, tv = torch.from_numpy(k).cuda().view(B * H, N, D), torch.from_numpy(v).cuda().view(B * H, N, D)
+    kb = torch.zeros((B * H, N, D), dtype=torch.float16, device="cuda")
+    vb = torch.zeros_like(kb)
+    tq = torch.from_numpy(np.ascontiguousarray(q[:, :, (nch - 1) * C:])).cuda()
+    out = torch.empty_like(tq)
+    ready = torch.zeros(nch, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    old = fa.set_sm_margin(8)      # a same-device copy may run as a kernel: leave it SMs next to the persistent grid
+    try:
+        fa.flash_attn_fwd_gathered(tq, kb.data_ptr(), vb.data_ptr(), out, N, N, True, (nch - 1) * C, ready, C)   # spins on ready[0]
+    finally:
+        fa.set_sm_margin(old)
+    with torch.cuda.stream(side):
+        for c in range(nch):
+            for h in range(B * H):
+                fa.peer_copy(kb[h, c * C:].data_ptr(), tk[h, c * C:].data_ptr(), C * D * 2, side)
+                fa.peer_copy(vb[h, c * C:].data_ptr(), tv[h, c * C:].data_ptr(), C * D * 2, side)
+            fa.stream_write_flag(ready.data_ptr() + 4 * c, 1, side)
+    torch.cuda.synchronize()
+    assert not fa.watchdog_status()["aborted"]
+    gate(out.cpu().numpy(), _oracle.attention(q, k, v, 1)[:, :, (nch - 1) * C:], "gathered, flags raised while the kernel runs")
+
+
 def test_split_mode_merges_slots_whose_references_differ(fa):
     """Even KV tiles hold small scores, odd ones large (and vice versa): the two slots end with very different reference
     maxima and the merge weights w = exp(m_s - max m) do the work."""
@@ -406,8 +471,8 @@ def test_peer_block_is_readable_from_another_process(fa):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (peer pulls over NVLink)")
 def test_context_parallel_pull_two_gpus_matches_monolithic():
-    """tests/harness/ring_check.py under torchrun: pull and sendrecv exchanges, causal and full, against the
-    monolithic kernel and oracle rows."""
+    """tests/harness/ring_check.py under torchrun: pull and sendrecv exchanges (causal and full) and the gathered form
+    (causal), against the monolithic kernel and oracle rows."""
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
@@ -415,7 +480,7 @@ def test_context_parallel_pull_two_gpus_matches_monolithic():
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
                         os.path.join(here, "harness", "ring_check.py"), "2048"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("PASS") == 8 and "FAIL" not in r.stdout
+    assert r.stdout.count("PASS") == 10 and "FAIL" not in r.stdout
 
 
 # ---- BF16 operands (flash_attn_fwd_bf16; the reference is FP16 only) ----

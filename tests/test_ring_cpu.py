@@ -230,3 +230,24 @@ def test_pull_plan_reads_distinct_owners_and_skips_masked_chunks():
             assert fetched == r + 2 * (world - 1 - r)
         full = ring.pull_plan(0, world, False)
         assert all(slots == [0, 1] and len(pairs) == 4 for _, slots, pairs in full)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_gathered_layout_gives_each_q_chunk_its_visible_keys_with_the_diagonal_last(world):
+    """exchange="gather": slot order of every rank's gathered K/V buffer (ring.gather_layout)."""
+    for r in range(world):
+        lay = ring.gather_layout(r, world)
+        ids = [o if w == 0 else 2 * world - 1 - o for o, w in lay]          # chunk ids in sequence order
+        lo, hi = ring.zigzag_chunks(r, world)
+        assert len(lay) == 2 * world - r and len(set(lay)) == len(lay)
+        assert ids[r] == lo and ids[-1] == hi                               # the diagonals close the two visible prefixes
+        assert sorted(ids[:r + 1]) == list(range(lo + 1))                   # low Q chunk: chunks 0 .. lo, nothing else
+        assert sorted(ids) == list(range(hi + 1))                           # high Q chunk: chunks 0 .. hi
+        # arrival order: hop h brings the chunks of rank r - h; P distinct owners are read at every hop
+        arrivals = [o for o, w in lay if o != r]
+        hops = [(r - o) % world for o in arrivals]
+        assert hops == sorted(hops)
+        for o, w in lay:
+            assert ring.gather_slot(r, world, o, w) == lay.index((o, w))
+    for hop in range(1, world):
+        assert sorted((r - hop) % world for r in range(world)) == list(range(world))
