@@ -261,9 +261,15 @@ class GatheredKV:
         handles = [None] * self.world
         dist.all_gather_object(handles, handle, group=group)
         self.peer_ptr = [self.ptr if r == self.rank else peer_open(handles[r]) for r in range(self.world)]
-        self.flags = torch.zeros(self.nslots, dtype=torch.int32, device=self.dev)
+        # A chunk may land in GATHER_PARTS row blocks with a ready flag each (FLASH_ATTN_GATHER_PARTS), and odd / even hops
+        # may pull on two copy streams side by side (FLASH_ATTN_GATHER_STREAMS=2).  Measured at 8 GPUs
+        # (profiles/r02_c12_gather_parts.log): K and V rows of a chunk on two streams 16.4 ms against 15.7 ms on one, and
+        # 16.6 / 16.8 ms with 2 / 4 blocks per chunk -- one block per chunk is the default.
+        self.parts = GATHER_PARTS if C % (128 * GATHER_PARTS) == 0 else 1
+        self.flags = torch.zeros(self.nslots * self.parts, dtype=torch.int32, device=self.dev)
         self.sync = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.comm = torch.cuda.Stream(device=self.dev)
+        self.comm2 = torch.cuda.Stream(device=self.dev) if GATHER_STREAMS == 2 else self.comm
 
     @property
     def k_ptr(self) -> int:
@@ -284,30 +290,39 @@ class GatheredKV:
             if mine.data_ptr() != given.data_ptr():
                 mine.copy_(given)
         self.flags.zero_()
-        self.flags[self.rank] = 1
-        self.flags[self.nslots - 1] = 1
+        nparts = self.parts
+        self.flags.view(self.nslots, nparts)[self.rank] = 1
+        self.flags.view(self.nslots, nparts)[self.nslots - 1] = 1
         dist.all_reduce(self.sync, group=self.group)             # stream-ordered behind the copies above
         self.comm.wait_stream(cur)
+        if self.comm2 is not self.comm:
+            self.comm2.wait_stream(cur)
         P, r = self.world, self.rank
         heads = self.B * self.H
+        part_bytes = self.chunk_row_bytes // nparts
         for hop in range(1, P):
             src = (r - hop) % P
             src_head_bytes = (2 * P - src) * self.chunk_row_bytes
             src_tensor_bytes = heads * src_head_bytes
+            stream = self.comm if hop % 2 == 1 else self.comm2    # two streams: odd and even hops pull side by side
             for which in ((0,) if src < r else (0, 1)):           # an owner behind us contributes only its low chunk
                 dst_slot = self.layout.index((src, which))
                 src_slot = src if which == 0 else 2 * P - src - 1
-                for t in range(2):                                 # K region, V region
-                    peer_copy_2d(self.ptr + t * self.tensor_bytes + dst_slot * self.chunk_row_bytes, self.head_bytes,
-                                 self.peer_ptr[src] + t * src_tensor_bytes + src_slot * self.chunk_row_bytes, src_head_bytes,
-                                 self.chunk_row_bytes, heads, self.comm)
-                stream_write_flag(self.flags.data_ptr() + 4 * dst_slot, 1, self.comm)
+                for part in range(nparts):
+                    for t in range(2):                             # K region, V region
+                        peer_copy_2d(self.ptr + t * self.tensor_bytes + dst_slot * self.chunk_row_bytes + part * part_bytes,
+                                     self.head_bytes,
+                                     self.peer_ptr[src] + t * src_tensor_bytes + src_slot * self.chunk_row_bytes + part * part_bytes,
+                                     src_head_bytes, part_bytes, heads, stream)
+                    stream_write_flag(self.flags.data_ptr() + 4 * (dst_slot * nparts + part), 1, stream)
 
     def end(self):
         """Everyone is done reading everyone's block: K/V may be rewritten after this (stream-ordered)."""
         import torch
         import torch.distributed as dist
         torch.cuda.current_stream(self.dev).wait_stream(self.comm)
+        if self.comm2 is not self.comm:
+            torch.cuda.current_stream(self.dev).wait_stream(self.comm2)
         dist.all_reduce(self.sync, group=self.group)
 
     def close(self):
@@ -322,6 +337,11 @@ class GatheredKV:
         self.k = self.v = self.block = None
         peer_free(self.ptr)
 
+
+# row blocks per chunk / copy streams of the gathered form (FLASH_ATTN_GATHER_PARTS, FLASH_ATTN_GATHER_STREAMS override)
+import os as _os
+GATHER_PARTS = int(_os.environ.get("FLASH_ATTN_GATHER_PARTS", "1"))
+GATHER_STREAMS = 2 if _os.environ.get("FLASH_ATTN_GATHER_STREAMS") == "2" else 1
 
 _gathered_kv: dict = {}
 
@@ -357,8 +377,9 @@ def gather_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool
     out = [torch.empty_like(q[0]), torch.empty_like(q[1])]
     # the low Q chunk first: it needs the slots that land first (the low chunks of the ranks behind us), so the pulls of the
     # later hops run under it; the high chunk's launch then finds most of its slots in place
-    flash_attn_fwd_gathered(q[0], gk.k_ptr, gk.v_ptr, out[0], (gk.rank + 1) * C, n * C, True, gk.rank * C, gk.flags, C)
-    flash_attn_fwd_gathered(q[1], gk.k_ptr, gk.v_ptr, out[1], n * C, n * C, True, (n - 1) * C, gk.flags, C)
+    rr = C // gk.parts                 # rows per ready flag
+    flash_attn_fwd_gathered(q[0], gk.k_ptr, gk.v_ptr, out[0], (gk.rank + 1) * C, n * C, True, gk.rank * C, gk.flags, rr)
+    flash_attn_fwd_gathered(q[1], gk.k_ptr, gk.v_ptr, out[1], n * C, n * C, True, (n - 1) * C, gk.flags, rr)
     gk.end()
     return out
 
