@@ -688,7 +688,10 @@ extern "C" int flash_attn_debug_status(unsigned int* out4) {
     if (e != cudaSuccess) return (int)e;
     return flash_attn_status(out4);
 }
-__global__ void fa_debug_trip_kernel(unsigned int tag) { sm100::watchdog_raise((int)tag); }
+__global__ void fa_debug_trip_kernel(unsigned int tag) {
+    sm100::watchdog_raise((int)tag);
+    sm100::watchdog_publish();
+}
 extern "C" int flash_attn_debug_trip_watchdog(unsigned int tag, void* stream) {
     int err = 0;
     if (!device_state(&err)) return err;

@@ -47,6 +47,8 @@
 //   -DFA_STREAM_S      second half of S re-read from TMEM instead of held in registers (r01_softmax_schedule.txt)
 //   -DFA_P_PARTS=3     P in three pieces;  -DFA_REGS_SOFTMAX / -DFA_REGS_OTHER  setmaxnreg budgets
 //                      (r01_v4b_defer_group_ab.log)
+//   -DFA_EPI_WG=1      epilogue warpgroup (512 threads; r02_c14_*: parity-clean, 4-8 % slower)
+//   -DFA_NO_WAIT_IN_VARIANT   the wait for S in front of the masked / unmasked branch instead of inside each (r02_c15_*)
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -64,20 +66,36 @@ using namespace sm100;
 
 constexpr int kBlockM = 128;      // Q rows per tile  (UMMA M)
 constexpr int kBlockN = 128;      // K/V rows per tile (UMMA N of QK^T, K extent of PV)
-constexpr int kNumThreads = 384;
 constexpr int kMmaWarp = 8;
 constexpr int kLoadWarp = 9;
 constexpr int kStoreWarp = 10;
 constexpr int kTmemCols = 512;
+// Epilogue warpgroup (experiment, -DFA_EPI_WG=1; off in the product build): warps 12-15 drain a finished O tile from TMEM
+// (O / l -> fp16 -> swizzled smem for the TMA store) while the softmax warps are already on the next work item, so an
+// item's epilogue (~2000 cycles: wait for the last PV, 128 columns through registers) leaves the softmax warps' chain.
+// Parity-clean on the whole GPU suite and 4-8 % SLOWER at D=128 (profiles/r02_c14_*): with 512 threads the register file
+// only allows 200/72/40 or 208/56/40 registers for softmax / MMA+producer / epilogue warps (spills in the softmax or the
+// MMA warp), and what the softmax warps gain is small because the next item's first S only exists ~1000 cycles after
+// the item's last PV anyway.
+#ifndef FA_EPI_WG
+#define FA_EPI_WG 0
+#endif
+constexpr bool kEpiWg = FA_EPI_WG != 0;
+constexpr int kEpiWarp0 = 12;
+constexpr int kNumThreads = kEpiWg ? 512 : 384;
 #ifndef FA_REGS_SOFTMAX
-#define FA_REGS_SOFTMAX 208
+#define FA_REGS_SOFTMAX (FA_EPI_WG ? 200 : 208)
 #endif
 #ifndef FA_REGS_OTHER
-#define FA_REGS_OTHER 80
+#define FA_REGS_OTHER (FA_EPI_WG ? 56 : 80)
 #endif
-constexpr int kRegsSoftmax = FA_REGS_SOFTMAX;   // setmaxnreg: softmax warpgroups grow, the producer/MMA warpgroup shrinks
-constexpr int kRegsOther = FA_REGS_OTHER;       // 2*128*208 + 128*80 = 63488 <= 168 (launch) * 384
-static_assert(2 * 128 * kRegsSoftmax + 128 * kRegsOther <= 65536, "register file");
+#ifndef FA_REGS_EPI
+#define FA_REGS_EPI 56
+#endif
+constexpr int kRegsSoftmax = FA_REGS_SOFTMAX;   // setmaxnreg: softmax warpgroups grow, the other warpgroups shrink
+constexpr int kRegsOther = FA_REGS_OTHER;       // without the epilogue warpgroup: 2*128*208 + 128*80 = 63488 <= 168 (launch) * 384
+constexpr int kRegsEpi = FA_REGS_EPI;           // with it: 2*128*200 + 128*56 + 128*56 = 65536 = 128 (launch) * 512
+static_assert(2 * 128 * kRegsSoftmax + 128 * kRegsOther + (kEpiWg ? 128 * kRegsEpi : 0) <= 65536, "register file");
 // P_t reaches the MMA warp in kPParts pieces (k-steps of 16 keys: [0,4) [4,8) or [0,4) [4,6) [6,8)): the PV k-steps of
 // a piece run under the exponentials of the next one, and only the last piece's k-steps sit between the end of the
 // softmax and the next QK^T of the tile.
@@ -113,9 +131,10 @@ struct Cfg {
     static constexpr int kSmemQ = 4 * kTileBytes;
     static constexpr int kSmemKV = kStages * kTileBytes;
     static constexpr int kBarOffset = kSmemQ + kSmemKV;
-    static constexpr int kNumBars = 4 + 2 * kStages + 14 + 4 + 4;
+    static constexpr int kNumBars = 4 + 2 * kStages + 14 + 4 + 4 + 4;
     static constexpr int kMlOffset = kBarOffset + kNumBars * 8 + 32;           // +32: tmem slot, scheduler slots
-    // hand-over area of split mode: (m, l) of tile slot 1, one pair per row
+    // hand-over area: split mode (m, l) of tile slot 1, one pair per row; pair mode with the epilogue warpgroup: the row
+    // sums l of the two tiles, one float per row
     static constexpr int kXchBytes = kBlockM * 8;
     // SWIZZLE_128B tiles need a 1024-byte aligned base; the dynamic window is that aligned on sm_100 in practice, the
     // slack (whatever is left of the 227 KB, at most 1 KB) covers a base that is not, and the kernel checks
@@ -502,34 +521,13 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     const float m_new = fmaxf(m_ref, m_tile);
 
     // Lazy rescale (replaces the reference's every-tile O *= alpha, FA.cu:267-270): the reference
-    // max only moves when the true max has outgrown it by 2^kRescaleThreshold.
+    // max only moves when the true max has outgrown it by 2^kRescaleThreshold.  Rare after a row's first tiles, so the
+    // block lives BEHIND the tile's straight-line code (label `rescale` below): inline it sat in the middle of the hot
+    // path, which then jumped 2.6 KB across it on every tile (stall_no_inst at the jump target, r02_final ncu capture).
     const bool need = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;  // NaN (-inf - -inf) -> false
-    if (__any_sync(0xffffffffu, need)) {
-        if (have_o) {
-            const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
-            const uint64_t alpha2 = pack_f32x2(alpha, alpha);
-            // O_t holds PV(0..j-1); the last of them must have retired before we touch it
-            mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 40);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < D; c += 32) {
-                uint32_t o[32];
-                tmem_ld_x32(tO + c, o);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float lo, hi;
-                    unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), lo, hi);
-                    o[i] = __float_as_uint(lo);
-                    o[i + 1] = __float_as_uint(hi);
-                }
-                tmem_st_x32(tO + c, o);
-            }
-            l_run *= alpha;
-        }
-        m_ref = m_new;
-    }
-
+    if (__any_sync(0xffffffffu, need)) goto rescale;
+resume:
+    {
     const float m_used = (m_ref == -INFINITY) ? 0.0f : m_ref;
     const float neg = -m_used * p.scale_log2;
     const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
@@ -597,6 +595,33 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     float a0, a1;
     unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
     l_run += a0 + a1;
+    return;
+    }
+rescale:
+    if (have_o) {
+        const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
+        const uint64_t alpha2 = pack_f32x2(alpha, alpha);
+        // O_t holds PV(0..j-1); the last of them must have retired before we touch it
+        mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 40);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + c, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                float lo, hi;
+                unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), lo, hi);
+                o[i] = __float_as_uint(lo);
+                o[i + 1] = __float_as_uint(hi);
+            }
+            tmem_st_x32(tO + c, o);
+        }
+        l_run *= alpha;
+    }
+    m_ref = m_new;
+    goto resume;
 }
 #endif  // FA_SUM_GUARD
 
@@ -719,6 +744,40 @@ __device__ __forceinline__ bool softmax_tile_stream(const Params& p, uint32_t tS
     return true;
 }
 
+// ---- plain epilogue of one O tile: TMEM -> registers -> O / l -> fp16 -> staging tile in shared memory ----
+// One thread per row (TMEM lane).  The staging tile is the item's idle Q tile buffer, 16-byte chunks XOR-swizzled by
+// row & 7 as TMA expects for SWIZZLE_128B; the caller orders the writes before the TMA store (fence.proxy.async).
+template <int D, bool kBF16, int kChunk = 32>
+__device__ __forceinline__ void stage_o_tile(uint32_t tO, uint32_t tile_smem, int row_in_tile, float l_run, bool have_o) {
+    using C = Cfg<D>;
+    static_assert(kChunk == 32 || kChunk == 16, "columns per TMEM load");
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;   // FA.cu:502-503
+    const uint32_t stage = tile_smem + row_in_tile * 128;
+#pragma unroll
+    for (int c = 0; c < D; c += kChunk) {
+        uint32_t o[kChunk];
+        if (have_o) {
+            if (kChunk == 32) tmem_ld_x32(tO + c, o);
+            else tmem_ld_x16(tO + c, o);
+            tmem_wait_ld();
+        } else {
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) o[i] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < kChunk; i += 8) {
+            const int col = c + i;
+            const uint32_t addr = stage + (col >> 6) * C::kPanelBytes + ((((col & 63) >> 3) ^ (row_in_tile & 7)) << 4);
+            const uint32_t v0 = pack_16x2<kBF16>(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
+            const uint32_t v1 = pack_16x2<kBF16>(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+            const uint32_t v2 = pack_16x2<kBF16>(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+            const uint32_t v3 = pack_16x2<kBF16>(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+            st_shared_v4(addr, v0, v1, v2, v3);
+        }
+    }
+    fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
+}
+
 template <int D, int kPoly, bool kBF16 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -728,7 +787,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     if (smem_base - smem_u32(smem_raw) + (uint32_t)(C::kMlOffset + C::kXchBytes) > (uint32_t)C::kSmemBytes) {
-        if (threadIdx.x == 0) watchdog_raise(99);     // dynamic window less aligned than the slack covers: refuse to run
+        if (threadIdx.x == 0) {                       // dynamic window less aligned than the slack covers: refuse to run
+            watchdog_raise(99);
+            watchdog_publish();
+        }
         return;
     }
     const uint32_t sQ = smem_base;
@@ -745,12 +807,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t bar_o_staged = bar_o_half + 16;                // [Q slot][tile] softmax warps -> store warp
     const uint32_t bar_sched_full = bar_o_staged + 32;            // [2] work-index slots, producer -> everyone
     const uint32_t bar_sched_empty = bar_sched_full + 16;         // [2]
-    const uint32_t tmem_slot = bar_sched_empty + 16;
+    const uint32_t bar_epi_full = bar_sched_empty + 16;           // [tile] softmax warps -> epilogue warpgroup: the item's row sums are in smem
+    const uint32_t bar_o_free = bar_epi_full + 16;                // [tile] epilogue warpgroup -> MMA warp / softmax warps: O_t and the l slots are drained
+    const uint32_t tmem_slot = bar_o_free + 16;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     volatile int* sched_w = reinterpret_cast<volatile int*>(tmem_slot_ptr + 2);   // [2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // the epilogue warpgroup takes the plain fp16 epilogue; the merge of split mode and the partial-state format stay with
+    // the softmax warps (their rows' (m, l) live in those warps' registers and both are short-sequence / per-hop paths)
+    const bool epi = kEpiWg && !p.split && !p.partial_mode;
 #ifdef FA_TIMING
     long long k_c0 = 0;
     unsigned long long k_t0 = 0;
@@ -776,12 +843,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 mbar_init(bar_p_full + 32 * t + 8 * part, 4);   // one arrival per softmax warp of the tile, per piece of P
             mbar_init(bar_o_full + 8 * t, 1);
             mbar_init(bar_o_half + 8 * t, 1);
-            mbar_init(bar_o_staged + 8 * t, 4);       // one arrival per softmax warp of the tile,
+            mbar_init(bar_o_staged + 8 * t, 4);       // one arrival per softmax (or epilogue) warp of the tile,
             mbar_init(bar_o_staged + 8 * (2 + t), 4); // per Q slot
+            mbar_init(bar_epi_full + 8 * t, 4);       // one arrival per softmax warp of the tile
+            mbar_init(bar_o_free + 8 * t, 4);         // one arrival per epilogue warp
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_sched_full + 8 * i, 1);
-            mbar_init(bar_sched_empty + 8 * i, 10);   // MMA warp + 8 softmax warps + store warp
+            mbar_init(bar_sched_empty + 8 * i, epi ? 14 : 10);   // MMA warp + 8 softmax warps + store warp (+ 4 epilogue warps)
         }
         fence_mbar_init();
     }
@@ -825,7 +894,55 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // flow keeps descriptors and barrier addresses in uniform registers -- in a lane-divergent
     // region every UTCHMMA costs an extra ELECT / R2UR.BROADCAST sequence and the single issuing
     // thread becomes the bottleneck of the whole CTA (profiles/r01_v1_full_n8192_summary.txt).
-    if (warp >= 8) {
+    if (kEpiWg && warp >= kEpiWarp0) {
+        setmaxnreg_dec<kRegsEpi>();
+        // =============================== epilogue warpgroup ===============================
+        // Warp 12 + q owns TMEM lanes [32q, 32q + 32) = rows 32q.. of whichever tile it drains.  Per work item and tile:
+        // wait until the tile's softmax warps have left their row sums in shared memory (epi_full) and the tile's last PV
+        // has retired (o_full), stage the fp16 rows for the store warp (o_staged), and give O_t and the l slots back
+        // (o_free: the MMA warp waits for it before the next item's first PV overwrites O_t, the softmax warps before
+        // they write the next item's row sums).  Tile 0 then tile 1: in steady state they finish half a period apart.
+        if (epi) {
+            const int q = warp & 3;
+            const int row_in_tile = q * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            uint32_t cnt0 = 0u, cnt1 = 0u;        // items drained so far, per tile
+            uint32_t pv0 = 0u, pv1 = 0u;          // PV MMAs issued so far, per tile == o_full completions to expect
+            for (uint32_t it = 0;; ++it) {
+                const int w = next_work(it);
+                if (w < 0) break;
+                const WorkItem wi = decode_work(w, p);
+                const uint32_t slot = it & 1u;
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    if (t == 1 && !wi.tile1) continue;                  // tile absent: nobody arrives, nothing to stage
+                    const int n_t = t ? wi.n1 : wi.n0;
+                    uint32_t& cnt = t ? cnt1 : cnt0;
+                    uint32_t& pv = t ? pv1 : pv0;
+                    mbar_wait(bar_epi_full + 8 * t, cnt & 1u, 36 + t);
+                    const float l_run = ld_shared_f32(smem_base + C::kMlOffset + (t * kBlockM + row_in_tile) * 4);
+                    if (n_t > 0) {
+                        pv += (uint32_t)n_t;
+                        mbar_wait(bar_o_full + 8 * t, (pv - 1u) & 1u, 30 + t);
+                        tc_fence_after();
+                    } else {
+                        // no key visible to the tile: nothing else has waited for the item's Q pair to land, and the rows
+                        // are staged in that very buffer (see the softmax warps' epilogue below)
+                        mbar_wait(bar_q_full + 8 * slot, (it >> 1) & 1u, 32 + t);
+                    }
+                    stage_o_tile<D, kBF16, kRegsEpi >= 56 ? 32 : 16>(tmem_base + lane_base + (t ? C::kTmemO1 : C::kTmemO0),
+                                           sQ + (slot * 2 + t) * C::kTileBytes, row_in_tile, l_run, n_t > 0);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(bar_o_free + 8 * t);
+                        mbar_arrive(bar_o_staged + 8 * (slot * 2 + t));
+                    }
+                    ++cnt;
+                }
+            }
+        }
+    } else if (warp >= 8) {
     setmaxnreg_dec<kRegsOther>();   // each role's code must be dominated by its own setmaxnreg
     if (warp == kLoadWarp) {
         // =============================== TMA producer ===============================
@@ -1029,6 +1146,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             wi = decode_work(w, p);
             prologue(0u, wi);
         }
+        uint32_t ocnt0 = 0u, ocnt1 = 0u;      // items so far in which tile t exists == o_free completions before this item
         for (; w >= 0; ++it) {
             const uint32_t slot = it & 1u;
             const int n0 = wi.n0, n1 = wi.n1;
@@ -1042,6 +1160,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 const uint32_t k_smem = sKV + rk.idx * C::kTileBytes;
                 // ---- tile 0: PV0(j), QK0(j+1)
                 if (j < n0) {
+                    // the epilogue warpgroup must have drained the previous item's O_0 before this PV overwrites it
+                    if (epi && j == 0 && ocnt0 > 0u) mbar_wait(bar_o_free, (ocnt0 - 1u) & 1u, 16);
                     issue_pv(tO0, tS0, v_smem, j > 0, bar_p_full, p_phase0, bar_o_full, bar_o_half, 13);
                     p_phase0 ^= 1u;
                 }
@@ -1052,6 +1172,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 if (j + 1 < n0) issue_qk(tS0, qdesc0, k_smem, bar_s_full);
                 // ---- tile 1: PV1(j), QK1(j+1)
                 if (j < n1) {
+                    if (epi && j == 0 && ocnt1 > 0u) mbar_wait(bar_o_free + 8, (ocnt1 - 1u) & 1u, 17);
                     issue_pv(tO1, tS1, v_smem, j > 0, bar_p_full + 32, p_phase1, bar_o_full + 8, bar_o_half + 8, 14);
                     p_phase1 ^= 1u;
                 }
@@ -1064,6 +1185,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     if (j + 2 == nmax) commit(bar_q_empty + 8 * slot);   // QK^T(nmax-1) was the last reader of Q
                 }
             }
+            ++ocnt0;
+            if (wi.tile1) ++ocnt1;
             // next item: its Q pair is already resident in the other slot
             w = next_work(it + 1u);
             if (w >= 0) {
@@ -1119,6 +1242,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const uint32_t my_o_half = bar_o_half + 8 * t;
         uint32_t s_phase = 0;
         uint32_t pv_count = 0;   // P tiles handed to the MMA warp so far == o_full completions expected
+        uint32_t epi_count = 0;  // items handed to the epilogue warpgroup so far
 
         for (uint32_t it = 0;; ++it) {
             const int w = next_work(it);
@@ -1139,6 +1263,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const long long ti0 = clock64();
 #endif
             for (int j = 0; j < n_t; j++) {
+#if !defined(FA_NO_WAIT_IN_VARIANT) && !defined(FA_TIMING) && !defined(FA_STREAM) && !defined(FA_SUM_GUARD)
+                // The wait for S sits inside each variant's branch, directly in front of that variant's code: the warp spins
+                // in the cache lines that precede the body it is about to run instead of jumping into a cold line once S
+                // arrives (stall_no_inst at the head of softmax_tile: 4 % of the softmax warps' samples, r02_final ncu capture).
+                {
+                    const int k0 = (p.split ? 2 * j + t : j) * kBlockN;
+                    const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
+                    if (need_mask) {
+                        mbar_wait(my_s_full, s_phase, 20 + t);
+                        tc_fence_after();
+                        softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, lim - k0, j > 0, pv_count, m_ref, l_run);
+                    } else {
+                        mbar_wait(my_s_full, s_phase, 22 + t);
+                        tc_fence_after();
+                        softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, kBlockN, j > 0, pv_count, m_ref, l_run);
+                    }
+                    s_phase ^= 1u;
+                    ++pv_count;
+                    continue;
+                }
+#endif
 #ifdef FA_TIMING
                 const long long tw0 = clock64();
 #endif
@@ -1190,6 +1335,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #ifdef FA_TIMING
             const long long ti_ep = clock64();
 #endif
+            if (epi) {
+                // The epilogue warpgroup drains O_t; this row's part is its sum.  The slot is free once that warpgroup has
+                // finished the tile's previous item (always the case by now unless this item had no visible key at all).
+                if (epi_count > 0u) mbar_wait(bar_o_free + 8 * t, (epi_count - 1u) & 1u, 34 + t);
+                ++epi_count;
+                st_shared_f32(smem_base + C::kMlOffset + (t * kBlockM + row_in_tile) * 4, l_run);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_epi_full + 8 * t);
+#ifdef FA_TIMING
+                if (lane == 0 && (warp & 3) == 0) {
+                    atomicAdd(&g_timing[14 + t], (unsigned long long)(clock64() - ti_ep));
+                    atomicAdd(&g_timing[16 + t], (unsigned long long)(clock64() - ti0));   // whole item
+                }
+#endif
+                continue;
+            }
             if (n_t > 0) {
                 mbar_wait(my_o_full, (pv_count - 1u) & 1u, 30 + t);
                 tc_fence_after();
@@ -1274,32 +1435,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 }
                 fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
             } else if (!p.partial_mode) {
-                const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;   // FA.cu:502-503
-                // fp16 row -> staging tile = this item's Q tile buffer (every QK^T of the item has retired:
-                // o_full covers them), 16-byte chunks XOR-swizzled by row & 7 as TMA expects for SWIZZLE_128B
-                const uint32_t stage = sQ + ((it & 1u) * 2 + t) * C::kTileBytes + row_in_tile * 128;
-#pragma unroll
-                for (int c = 0; c < D; c += 32) {
-                    uint32_t o[32];
-                    if (n_t > 0) {
-                        tmem_ld_x32(tO + c, o);
-                        tmem_wait_ld();
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; i++) o[i] = 0u;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-                        const int col = c + i;
-                        const uint32_t addr = stage + (col >> 6) * C::kPanelBytes + ((((col & 63) >> 3) ^ (row_in_tile & 7)) << 4);
-                        const uint32_t v0 = pack_16x2<kBF16>(__uint_as_float(o[i + 0]) * inv, __uint_as_float(o[i + 1]) * inv);
-                        const uint32_t v1 = pack_16x2<kBF16>(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-                        const uint32_t v2 = pack_16x2<kBF16>(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-                        const uint32_t v3 = pack_16x2<kBF16>(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-                        st_shared_v4(addr, v0, v1, v2, v3);
-                    }
-                }
-                fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
+                // fp16 row -> staging tile = this item's Q tile buffer (every QK^T of the item has retired: o_full covers them)
+                if (!kEpiWg)
+                    stage_o_tile<D, kBF16>(tO, sQ + ((it & 1u) * 2 + t) * C::kTileBytes, row_in_tile, l_run, n_t > 0);
             } else {
                 // partial state (FA.cu:460-496): un-normalised fp32 O, (m, l) with m in the
                 // scaled-score (natural-log) domain; merge algebra of FA.cu:575-597 when accumulating
@@ -1406,6 +1544,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
 #endif
     if (threadIdx.x == 0) {
+        watchdog_publish();     // a waiter of this launch gave up: leave the record where the launcher's next call finds it
         // last CTA out re-arms the scheduler state for the launch that reuses this slot
         __threadfence();
         if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
