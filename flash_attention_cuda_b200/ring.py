@@ -270,6 +270,7 @@ class GatheredKV:
         self.sync = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.comm = torch.cuda.Stream(device=self.dev)
         self.comm2 = torch.cuda.Stream(device=self.dev) if GATHER_STREAMS == 2 else self.comm
+        self.side = torch.cuda.Stream(device=self.dev)           # second kernel stream (GATHER_OVERLAP)
 
     @property
     def k_ptr(self) -> int:
@@ -342,6 +343,9 @@ class GatheredKV:
 import os as _os
 GATHER_PARTS = int(_os.environ.get("FLASH_ATTN_GATHER_PARTS", "1"))
 GATHER_STREAMS = 2 if _os.environ.get("FLASH_ATTN_GATHER_STREAMS") == "2" else 1
+# the two kernels of a step on two streams (FLASH_ATTN_GATHER_OVERLAP=0 puts them back on one): the second grid fills SMs as the
+# first one drains -- 15.2-15.4 ms against 15.7-15.9 ms per step at 8 GPUs (profiles/r02_final_8gpu_gather_overlap.log)
+GATHER_OVERLAP = _os.environ.get("FLASH_ATTN_GATHER_OVERLAP", "1") == "1"
 
 _gathered_kv: dict = {}
 
@@ -378,8 +382,19 @@ def gather_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool
     # the low Q chunk first: it needs the slots that land first (the low chunks of the ranks behind us), so the pulls of the
     # later hops run under it; the high chunk's launch then finds most of its slots in place
     rr = C // gk.parts                 # rows per ready flag
-    flash_attn_fwd_gathered(q[0], gk.k_ptr, gk.v_ptr, out[0], (gk.rank + 1) * C, n * C, True, gk.rank * C, gk.flags, rr)
-    flash_attn_fwd_gathered(q[1], gk.k_ptr, gk.v_ptr, out[1], n * C, n * C, True, (n - 1) * C, gk.flags, rr)
+    if GATHER_OVERLAP:
+        # The two kernels are independent (different Q chunk, different output): the high chunk's launch goes to a second
+        # stream so that its CTAs take over SM by SM as the low chunk's persistent CTAs run out of work, instead of waiting
+        # for the whole grid to drain (work items here are 0.1 ms per slot: the tail of a launch is not small)
+        cur = torch.cuda.current_stream(q[0].device)
+        gk.side.wait_stream(cur)
+        flash_attn_fwd_gathered(q[0], gk.k_ptr, gk.v_ptr, out[0], (gk.rank + 1) * C, n * C, True, gk.rank * C, gk.flags, rr)
+        with torch.cuda.stream(gk.side):
+            flash_attn_fwd_gathered(q[1], gk.k_ptr, gk.v_ptr, out[1], n * C, n * C, True, (n - 1) * C, gk.flags, rr)
+        cur.wait_stream(gk.side)
+    else:
+        flash_attn_fwd_gathered(q[0], gk.k_ptr, gk.v_ptr, out[0], (gk.rank + 1) * C, n * C, True, gk.rank * C, gk.flags, rr)
+        flash_attn_fwd_gathered(q[1], gk.k_ptr, gk.v_ptr, out[1], n * C, n * C, True, (n - 1) * C, gk.flags, rr)
     gk.end()
     return out
 
