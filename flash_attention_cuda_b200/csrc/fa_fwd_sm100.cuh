@@ -49,6 +49,9 @@
 //                      (r01_v4b_defer_group_ab.log)
 //   -DFA_EPI_WG=1      epilogue warpgroup (512 threads; r02_c14_*: parity-clean, 4-8 % slower)
 //   -DFA_NO_WAIT_IN_VARIANT   the wait for S in front of the masked / unmasked branch instead of inside each (r02_c15_*)
+//   -DFA_NO_SCALE_REG / -DFA_NO_PIN_ADDR   scale, S address and p_full barrier address re-materialised per tile (r02_c21_*, r02_c22_*)
+//   -DFA_SPEC          piece 0's exponentials against the row's current reference, vote afterwards (softmax_tile_spec;
+//                      parity-clean, 0 to -4 %: r02_c21_*)
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -248,6 +251,14 @@ __device__ __forceinline__ uint64_t sched_fence(uint64_t v, int zero) {
 #endif
 }
 
+// A value ptxas may not rematerialise (it would rather recompute an address or re-load a kernel parameter in every tile
+// than hold a register): OR-ed with (%clock & zero), zero being the kernel parameter that is always 0.
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v, int zero) {
+    uint32_t c;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+    return v | (c & (uint32_t)zero);
+}
+
 struct Ring {
     uint32_t idx, phase;
     template <int kStages>
@@ -383,7 +394,7 @@ __device__ __forceinline__ float hsum_f32x2(uint64_t a, uint64_t b) {
 template <int D, bool kMask, int kPoly, bool kBF16>
 __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
                                              uint32_t bar_o_full, uint32_t bar_o_half, int lim_local, bool have_o,
-                                             uint32_t pv_count, float& m_ref, float& l_run) {
+                                             uint32_t pv_count, float& m_ref, float& l_run, float /*sl2*/ = 0.f) {
     static_assert(kPParts == 2, "the sum-guarded softmax delivers P in two pieces");
     uint32_t s[kBlockN];
     tmem_ld_x32(tS + 0, s + 0);
@@ -491,7 +502,9 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
 template <int D, bool kMask, int kPoly, bool kBF16>
 __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
                                              uint32_t bar_o_full, uint32_t /*bar_o_half*/, int lim_local, bool have_o,
-                                             uint32_t pv_count, float& m_ref, float& l_run) {
+                                             uint32_t pv_count, float& m_ref, float& l_run, float sl2) {
+    // sl2 = sl2: an argument so that the caller can pin it in a register (-DFA_SCALE_REG) instead of the tile
+    // re-loading it from the constant bank between the row max and the first exponential
     uint32_t s[kBlockN];
     tmem_ld_x32(tS + 0, s + 0);
     tmem_ld_x32(tS + 32, s + 32);
@@ -524,13 +537,13 @@ __device__ __forceinline__ void softmax_tile(const Params& p, uint32_t tS, uint3
     // max only moves when the true max has outgrown it by 2^kRescaleThreshold.  Rare after a row's first tiles, so the
     // block lives BEHIND the tile's straight-line code (label `rescale` below): inline it sat in the middle of the hot
     // path, which then jumped 2.6 KB across it on every tile (stall_no_inst at the jump target, r02_final ncu capture).
-    const bool need = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;  // NaN (-inf - -inf) -> false
+    const bool need = (m_new - m_ref) * sl2 > kRescaleThreshold;  // NaN (-inf - -inf) -> false
     if (__any_sync(0xffffffffu, need)) goto rescale;
 resume:
     {
     const float m_used = (m_ref == -INFINITY) ? 0.0f : m_ref;
-    const float neg = -m_used * p.scale_log2;
-    const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+    const float neg = -m_used * sl2;
+    const uint64_t scale2 = pack_f32x2(sl2, sl2);
     const uint64_t neg2 = pack_f32x2(neg, neg);
     uint64_t sum_a = 0ull, sum_b = 0ull;     // (0.f, 0.f)
     uint32_t pk[32];
@@ -599,7 +612,7 @@ resume:
     }
 rescale:
     if (have_o) {
-        const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * p.scale_log2);
+        const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * sl2);
         const uint64_t alpha2 = pack_f32x2(alpha, alpha);
         // O_t holds PV(0..j-1); the last of them must have retired before we touch it
         mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 40);
@@ -624,6 +637,107 @@ rescale:
     goto resume;
 }
 #endif  // FA_SUM_GUARD
+
+// ---- softmax_tile with the reference decision off the critical path (-DFA_SPEC) ----
+// softmax_tile cannot start an exponential before the 61-deep FMNMX3 row max, the compare against the reference, a warp vote
+// and a branch have all resolved: ~250 cycles of ALU-pipe work plus ~100 cycles of serial latency per tile during which the
+// FMA pipe and the SFU idle (profiles/r02_softmax_hot_loop.sass.txt).  After a row's first tiles the vote says "keep the
+// reference" almost always, so this form starts the first piece's exponentials against the reference the row already has,
+// with the row max computed in the same basic block (ptxas interleaves the two), and votes afterwards: a tile whose max has
+// outgrown the reference by 2^kRescaleThreshold rescales O as before and runs the piece again (the loop below re-enters the
+// same code: nothing is duplicated).  Same instructions on the hot path, same results bit for bit.
+template <int kFrom, int kTo>
+__device__ __forceinline__ float row_max_of(const uint32_t* s) {
+    float mx0 = fmaxf(__uint_as_float(s[kFrom + 0]), __uint_as_float(s[kFrom + 1]));
+    float mx1 = fmaxf(__uint_as_float(s[kFrom + 2]), __uint_as_float(s[kFrom + 3]));
+    float mx2 = fmaxf(__uint_as_float(s[kFrom + 4]), __uint_as_float(s[kFrom + 5]));
+    float mx3 = fmaxf(__uint_as_float(s[kFrom + 6]), __uint_as_float(s[kFrom + 7]));
+#pragma unroll
+    for (int i = kFrom + 8; i < kTo; i += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+    }
+    return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+}
+
+template <int D, bool kMask, int kPoly, bool kBF16>
+__device__ __forceinline__ void softmax_tile_spec(const Params& p, uint32_t tS, uint32_t tO, uint32_t bar_p_full,
+                                                  uint32_t bar_o_full, int lim_local, uint32_t pv_count,
+                                                  float& m_ref, float& l_run, float sl2) {
+    static_assert(kPParts == 2, "two pieces of P");
+    uint32_t s[kBlockN];
+    tmem_ld_x32(tS + 0, s + 0);
+    tmem_ld_x32(tS + 32, s + 32);
+    tmem_ld_x32(tS + 64, s + 64);
+    tmem_ld_x32(tS + 96, s + 96);
+    tmem_wait_ld();
+    if (kMask) {
+#pragma unroll
+        for (int i = 0; i < kBlockN; i++)
+            if (i >= lim_local) s[i] = 0xff800000u;  // -inf
+    }
+    // (a row's first tile has no reference to speculate on and no O to rescale: the caller runs it through softmax_tile)
+    const uint64_t scale2 = pack_f32x2(sl2, sl2);
+    uint64_t neg2, sum_a, sum_b;
+    uint32_t pk[32];
+    float m_new = m_ref;
+    bool again = false;
+    // bottom-tested on purpose: the body (piece 0's exponentials + the row max) exists once; a pass that follows a rescale
+    // ends at the vote because then m_ref == m_new
+#pragma unroll 1
+    do {
+        if (again) {
+            // rare: the reference moves, O and l follow (FA.cu:267-270), the piece is computed again
+            const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_ref - m_new) * sl2);
+            const uint64_t alpha2 = pack_f32x2(alpha, alpha);
+            mbar_wait(bar_o_full, (pv_count - 1u) & 1u, 40);   // O_t holds PV(0..j-1); the last of them must have retired
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < D; c += 32) {
+                uint32_t o[32];
+                tmem_ld_x32(tO + c, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float lo, hi;
+                    unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), lo, hi);
+                    o[i] = __float_as_uint(lo);
+                    o[i + 1] = __float_as_uint(hi);
+                }
+                tmem_st_x32(tO + c, o);
+            }
+            l_run *= alpha;
+            m_ref = m_new;
+        }
+        const float m_used = (m_ref == -INFINITY) ? 0.0f : m_ref;
+        const float neg = -m_used * sl2;
+        neg2 = pack_f32x2(neg, neg);
+        sum_a = 0ull;
+        sum_b = 0ull;
+        exp_half<kPoly, kBF16>(s, pk, scale2, neg2, sum_a, sum_b);
+        m_new = fmaxf(m_ref, row_max_of<0, kBlockN>(s));
+        const bool need = (m_new - m_ref) * sl2 > kRescaleThreshold;  // NaN (-inf - -inf) -> false
+        again = __any_sync(0xffffffffu, need);
+    } while (again);
+    auto publish = [&](int part) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(bar_p_full + 8 * part);   // one arrival per warp (barrier count 4)
+    };
+    tmem_st_x32(tS, pk);
+    uint32_t pk2[32];
+    exp_half<kPoly, kBF16, 32>(s + 64, pk2, scale2, neg2, sum_a, sum_b);
+    publish(0);
+    exp_half<kPoly, kBF16, 32>(s + 96, pk2 + 16, scale2, neg2, sum_a, sum_b);
+    tmem_st_x32(tS + 32, pk2);
+    publish(1);
+    float a0, a1;
+    unpack_f32x2(add_f32x2(sum_a, sum_b), a0, a1);
+    l_run += a0 + a1;
+}
 
 // ---- streamed softmax of one 128x128 S tile (one thread per row) ----
 // softmax_tile above cannot start an exponential before all 128 columns of the row have crossed the TMEM read
@@ -1234,14 +1348,28 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int t = warp >> 2;                               // which Q tile of the pair
         const int row_in_tile = (warp & 3) * 32 + lane;        // TMEM lane == S/O row
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+#ifndef FA_NO_PIN_ADDR
+        // pinned (pin_u32): ptxas otherwise rebuilds both addresses in every tile from %tid / the shared-window base
+        // (S2R, LEA, LOP3 ... ~10 instructions per tile on each softmax warp): +0.6 % at N=8192, +2.8 % at causal N=2048
+        const uint32_t tS = pin_u32(tmem_base + lane_base + (t ? C::kTmemS1 : C::kTmemS0), p.zero);
+        const uint32_t my_p_full = pin_u32(bar_p_full + 32 * t, p.zero);        // + 8 * piece
+#else
         const uint32_t tS = tmem_base + lane_base + (t ? C::kTmemS1 : C::kTmemS0);
+        const uint32_t my_p_full = bar_p_full + 32 * t;        // + 8 * piece
+#endif
         const uint32_t tO = tmem_base + lane_base + (t ? C::kTmemO1 : C::kTmemO0);
         const uint32_t my_s_full = bar_s_full + 8 * t;
-        const uint32_t my_p_full = bar_p_full + 32 * t;        // + 8 * piece
         const uint32_t my_o_full = bar_o_full + 8 * t;
         const uint32_t my_o_half = bar_o_half + 8 * t;
         uint32_t s_phase = 0;
         uint32_t pv_count = 0;   // P tiles handed to the MMA warp so far == o_full completions expected
+        // p.scale_log2 pinned in a register: ptxas otherwise re-loads it from the constant bank in every tile, between the
+        // row max and the first exponential (LDC + scoreboard wait on the S -> P chain).  The OR with (clock & p.zero) --
+        // p.zero is always 0 -- makes the value opaque, so it cannot be rematerialised: +0.6-1.3 % (profiles/r02_c21_*)
+        float sl2 = p.scale_log2;
+#ifndef FA_NO_SCALE_REG
+        sl2 = __uint_as_float(pin_u32(__float_as_uint(sl2), p.zero));
+#endif
         uint32_t epi_count = 0;  // items handed to the epilogue warpgroup so far
 
         for (uint32_t it = 0;; ++it) {
@@ -1270,15 +1398,30 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 {
                     const int k0 = (p.split ? 2 * j + t : j) * kBlockN;
                     const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
-                    if (need_mask) {
+#ifdef FA_SPEC
+                    // masked tiles and a row's first tile take the classic form (mask limit kBlockN = no mask), every other
+                    // tile the speculative one: two softmax bodies in the kernel, as before
+                    if (need_mask || j == 0) {
                         mbar_wait(my_s_full, s_phase, 20 + t);
                         tc_fence_after();
-                        softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, lim - k0, j > 0, pv_count, m_ref, l_run);
+                        softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, need_mask ? lim - k0 : kBlockN,
+                                                            j > 0, pv_count, m_ref, l_run, sl2);
                     } else {
                         mbar_wait(my_s_full, s_phase, 22 + t);
                         tc_fence_after();
-                        softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, kBlockN, j > 0, pv_count, m_ref, l_run);
+                        softmax_tile_spec<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, kBlockN, pv_count, m_ref, l_run, sl2);
                     }
+#else
+                    if (need_mask) {
+                        mbar_wait(my_s_full, s_phase, 20 + t);
+                        tc_fence_after();
+                        softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, lim - k0, j > 0, pv_count, m_ref, l_run, sl2);
+                    } else {
+                        mbar_wait(my_s_full, s_phase, 22 + t);
+                        tc_fence_after();
+                        softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, kBlockN, j > 0, pv_count, m_ref, l_run, sl2);
+                    }
+#endif
                     s_phase ^= 1u;
                     ++pv_count;
                     continue;
@@ -1302,9 +1445,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
 #if !defined(FA_STREAM) || defined(FA_SUM_GUARD)
                 if (need_mask)
-                    softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, lim - k0, j > 0, pv_count, m_ref, l_run);
+                    softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, lim - k0, j > 0, pv_count, m_ref, l_run, sl2);
                 else
-                    softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, kBlockN, j > 0, pv_count, m_ref, l_run);
+                    softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, kBlockN, j > 0, pv_count, m_ref, l_run, sl2);
 #else
                 // streamed softmax; a tile whose scores outgrew the reference max by more than 2^15 (warp vote)
                 // is redone by the classic form, which takes the whole row's max first
@@ -1314,7 +1457,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     : softmax_tile_stream<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, kBlockN, last, pv_count, m_ref, l_run);
                 if (!done)
                     softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half,
-                                                        need_mask ? lim - k0 : kBlockN, j > 0, pv_count, m_ref, l_run);
+                                                        need_mask ? lim - k0 : kBlockN, j > 0, pv_count, m_ref, l_run, sl2);
 #endif
                 ++pv_count;
 #ifdef FA_TIMING

@@ -66,9 +66,9 @@ bench(Params p, unsigned long long* out, int iters, int active_mask, int offset1
 #ifdef BENCH_STREAM
             // the kernel's streamed form (S read in four chunks, exponentials against the row's current reference)
             if (!softmax_tile_stream<128, false, kPoly, false>(p, tS, tO, bar_p, bar_o, 128, true, pv, m_ref, l_run))
-                softmax_tile<128, true, kPoly, false>(p, tS, tO, bar_p, bar_o, bar_oh, 128, it > 0, pv, m_ref, l_run);
+                softmax_tile<128, true, kPoly, false>(p, tS, tO, bar_p, bar_o, bar_oh, 128, it > 0, pv, m_ref, l_run, p.scale_log2);
 #else
-            softmax_tile<128, false, kPoly, false>(p, tS, tO, bar_p, bar_o, bar_oh, 128, it > 0, pv, m_ref, l_run);
+            softmax_tile<128, false, kPoly, false>(p, tS, tO, bar_p, bar_o, bar_oh, 128, it > 0, pv, m_ref, l_run, p.scale_log2);
 #endif
             const long long t1 = clock64();
             ++pv;
