@@ -68,7 +68,7 @@ DEFAULT_WORKLOAD = "cfg2_n8192_causal"
 NOMINAL_FP16_TFLOPS = 2250.0
 L2_BYTES = 126e6
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of OUR kernel, from the committed `ncu --set full` capture
-NCU_CAPTURES = {"cfg2_n8192_causal": "r01_v4c_causal_n8192_summary.txt"}
+NCU_CAPTURES = {"cfg2_n8192_causal": "r02_final_causal_n8192_summary.txt"}
 
 
 def flops(B, H, N, D, causal):
