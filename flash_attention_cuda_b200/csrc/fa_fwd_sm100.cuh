@@ -1391,35 +1391,64 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const long long ti0 = clock64();
 #endif
             for (int j = 0; j < n_t; j++) {
-#if !defined(FA_NO_WAIT_IN_VARIANT) && !defined(FA_TIMING) && !defined(FA_STREAM) && !defined(FA_SUM_GUARD)
+#if !defined(FA_NO_WAIT_IN_VARIANT) && !defined(FA_STREAM) && !defined(FA_SUM_GUARD)
                 // The wait for S sits inside each variant's branch, directly in front of that variant's code: the warp spins
                 // in the cache lines that precede the body it is about to run instead of jumping into a cold line once S
                 // arrives (stall_no_inst at the head of softmax_tile: 4 % of the softmax warps' samples, r02_final ncu capture).
                 {
                     const int k0 = (p.split ? 2 * j + t : j) * kBlockN;
                     const bool need_mask = (k0 + kBlockN > p.Nkv) || (p.causal && k0 + kBlockN - 1 > q_start + p.shift);
+#ifdef FA_TIMING
+                    const long long tw0 = clock64();
+                    long long tw1 = 0;
+#define FA_TW1 tw1 = clock64();
+#else
+#define FA_TW1
+#endif
 #ifdef FA_SPEC
                     // masked tiles and a row's first tile take the classic form (mask limit kBlockN = no mask), every other
                     // tile the speculative one: two softmax bodies in the kernel, as before
                     if (need_mask || j == 0) {
                         mbar_wait(my_s_full, s_phase, 20 + t);
                         tc_fence_after();
+                        FA_TW1
                         softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, need_mask ? lim - k0 : kBlockN,
                                                             j > 0, pv_count, m_ref, l_run, sl2);
                     } else {
                         mbar_wait(my_s_full, s_phase, 22 + t);
                         tc_fence_after();
+                        FA_TW1
                         softmax_tile_spec<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, kBlockN, pv_count, m_ref, l_run, sl2);
                     }
 #else
                     if (need_mask) {
                         mbar_wait(my_s_full, s_phase, 20 + t);
                         tc_fence_after();
+                        FA_TW1
                         softmax_tile<D, true, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, lim - k0, j > 0, pv_count, m_ref, l_run, sl2);
                     } else {
                         mbar_wait(my_s_full, s_phase, 22 + t);
                         tc_fence_after();
+                        FA_TW1
                         softmax_tile<D, false, kPoly, kBF16>(p, tS, tO, my_p_full, my_o_full, my_o_half, kBlockN, j > 0, pv_count, m_ref, l_run, sl2);
+                    }
+#endif
+#undef FA_TW1
+#ifdef FA_TIMING
+                    if (j == 0 && lane == 0 && (warp & 3) == 0) {     // item start -> first S of the item
+                        atomicAdd(&g_timing[8 + t * 2], (unsigned long long)(tw1 - ti0));
+                        atomicAdd(&g_timing[9 + t * 2], 1ull);
+                        if (it == 0) atomicAdd(&g_timing[12 + t], (unsigned long long)(tw1 - k_c0_all));   // kernel start -> first S
+                    }
+#ifdef FA_TIMING_ALL
+                    if (lane == 0 && (warp & 3) == 0 && j > 0) {                   // short sequences: every tile but the first
+#else
+                    if (lane == 0 && (warp & 3) == 0 && j > 0 && (j & 7) == 0) {   // sampled: 1 tile in 8
+#endif
+                        const long long tw2 = clock64();
+                        atomicAdd(&g_timing[t * 3 + 0], (unsigned long long)(tw1 - tw0));
+                        atomicAdd(&g_timing[t * 3 + 1], (unsigned long long)(tw2 - tw1));
+                        atomicAdd(&g_timing[t * 3 + 2], 1ull);
                     }
 #endif
                     s_phase ^= 1u;

@@ -1,5 +1,5 @@
 """Per-tile softmax timing of a -DFA_TIMING build: cycles a softmax warp waits for S vs cycles from
-S-ready to P-arrive.   FLASH_ATTN_B200_LIB=build/libfa_t1.so python tests/harness/timing.py [N] [causal]"""
+S-ready to P-arrive.   FLASH_ATTN_B200_LIB=build/lib_timing.so python tests/harness/timing.py [N] [causal] [B] [H] [D]"""
 import ctypes
 import os
 import sys
@@ -11,11 +11,12 @@ import flash_attention_cuda_b200 as fa  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 causal = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
+B, H, D = (int(sys.argv[i]) if len(sys.argv) > i else d for i, d in ((3, 1), (4, 32), (5, 128)))
 L = fa.lib()
 L.flash_attn_debug_timing.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 buf = (ctypes.c_ulonglong * 64)()
 g = torch.Generator(device="cuda").manual_seed(0)
-q, k, v = ((torch.rand((1, 32, N, 128), device="cuda", generator=g) - 0.5).half() for _ in range(3))
+q, k, v = ((torch.rand((B, H, N, D), device="cuda", generator=g) - 0.5).half() for _ in range(3))
 o = torch.empty_like(q)
 for _ in range(3):
     fa.flash_attn_fwd(q, k, v, causal=causal, out=o)
@@ -28,8 +29,8 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 L.flash_attn_debug_timing(buf, 0)
-fl = 4.0 * 32 * N * N * 128 / (2 if causal else 1)
-print(f"{os.path.basename(fa.LIB_PATH)} N={N} causal={causal}: {fl / ms / 1e9:.1f} TFLOPS")
+fl = 4.0 * B * H * N * N * D / (2 if causal else 1)
+print(f"{os.path.basename(fa.LIB_PATH)} B={B} H={H} N={N} D={D} causal={causal}: {fl / ms / 1e9:.1f} TFLOPS")
 for t in range(2):
     w, b, n = (buf[t * 3 + i] for i in range(3))
     if n:
