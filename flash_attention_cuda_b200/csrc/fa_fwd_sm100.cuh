@@ -943,6 +943,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #endif
 
     if (threadIdx.x == 0) {
+        *watchdog_block_flag() = 0u;
         for (int i = 0; i < 2; i++) {
             mbar_init(bar_q_full + 8 * i, 1);
             mbar_init(bar_q_empty + 8 * i, 2);        // last QK^T of the item retired + its O tiles stored
@@ -1073,6 +1074,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             if (lane == 0) {
                 sched_w[slot] = w;
                 mbar_arrive(bar_sched_full + 8 * slot);   // release: the slot write is visible to waiters
+                // This CTA will not claim again.  The last CTA to get here re-arms the scheduler words for the launch that
+                // reuses this slot (nobody claims any more: every claim above returned before its CTA counted itself).
+                // Done here, under the last item's work, and not on the CTA's exit path: a fence + atomic round trip there
+                // cost every launch ~1 us of tail.
+                if (w < 0 && atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+                    p.sched[0] = 0;
+                    p.sched[1] = 0;
+                }
             }
             __syncwarp();
             if (w < 0) break;
@@ -1339,6 +1348,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
             __syncwarp();
         }
+        // (exiting on wait_group.read alone -- the writes complete with the grid -- measured the same: profiles/r02_c26_*)
         if (lane == 0) tma_store_wait_all<0>();
         __syncwarp();
     }
@@ -1715,16 +1725,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         atomicAdd(&g_timing[22], 1ull);
     }
 #endif
-    if (threadIdx.x == 0) {
-        watchdog_publish();     // a waiter of this launch gave up: leave the record where the launcher's next call finds it
-        // last CTA out re-arms the scheduler state for the launch that reuses this slot
-        __threadfence();
-        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
-            p.sched[0] = 0;
-            p.sched[1] = 0;
-            __threadfence();
-        }
-    }
+    // a waiter of this CTA gave up: leave the record where the launcher's next call finds it
+    if (threadIdx.x == 0 && *reinterpret_cast<volatile unsigned int*>(watchdog_block_flag()) != 0u) watchdog_publish();
     if (warp == kMmaWarp) {
         __syncwarp();
         tc_fence_after();
