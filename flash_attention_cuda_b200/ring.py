@@ -492,7 +492,8 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
     """Context-parallel forward.  q, k, v: pairs (low chunk, high chunk) of contiguous [B, H, C, D] tensors in
     the zig-zag layout of `zigzag_chunks`.  Returns the pair of output chunks, same layout as q.
 
-    exchange = "pull" (CUDA default; FLASH_ATTN_RING_EXCHANGE overrides) or "sendrecv" (module docstring).
+    exchange = "gather" (CUDA default under a causal mask), "pull" (CUDA default without one) or "sendrecv" (module
+    docstring); FLASH_ATTN_RING_EXCHANGE overrides the default.
     sendrecv, each hop: post isend/irecv of the K/V pair for the next hop, run the (at most four, causal: two)
     chunk-pair kernels of this hop, wait for the transfer, swap buffers."""
     import os
@@ -501,11 +502,16 @@ def ring_attention_forward(q: Sequence, k: Sequence, v: Sequence, causal: bool, 
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    if exchange is None:
+        # CUDA default: the gathered form under a causal mask (no partial states, no merge), peer pulls with one partial
+        # state per chunk pair without one (the gathered layout relies on every slot but the last being entirely visible)
+        on_gpus = q[0].is_cuda and world > 1
+        plain = partial is None and finalize is None          # caller-supplied partial / finalize hooks go with pull / sendrecv
+        exchange = os.environ.get("FLASH_ATTN_RING_EXCHANGE") or \
+            ("sendrecv" if not on_gpus else "gather" if causal and plain else "pull")
     if exchange == "gather":               # K/V may be the strided views of the gathered buffer itself
         return gather_attention_forward(q, k, v, causal, group)
     _check_chunks(q, k, v)
-    if exchange is None:
-        exchange = os.environ.get("FLASH_ATTN_RING_EXCHANGE") or ("pull" if q[0].is_cuda and world > 1 else "sendrecv")
     if exchange not in ("pull", "sendrecv"):
         raise ValueError(f"exchange must be 'pull', 'gather' or 'sendrecv', not {exchange!r}")
     if exchange == "pull":

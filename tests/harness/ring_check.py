@@ -25,13 +25,14 @@ g = torch.Generator(device="cuda").manual_seed(99)          # identical global t
 q, k = (torch.randn((B, H, N, D), device="cuda", generator=g).half() for _ in range(2))
 v = (torch.randn((B, H, N, D), device="cuda", generator=g) * 0.5).half()
 ok = True
-EXCHANGES = sys.argv[2].split(",") if len(sys.argv) > 2 else ["pull", "sendrecv", "gather"]
+EXCHANGES = sys.argv[2].split(",") if len(sys.argv) > 2 else ["pull", "sendrecv", "gather", "default"]
 for causal, exchange in [(c, e) for e in EXCHANGES for c in (True, False) if c or e != "gather"]:   # gather: causal only
+    # "default": whatever ring_attention_forward picks on its own (gather under a causal mask, pull without one)
     full = fa.flash_attn_fwd(q, k, v, causal=causal)
     C = N // (2 * world)
     lo, hi = ring.zigzag_chunks(rank, world)
     ch = lambda x: [x[:, :, c * C:(c + 1) * C].contiguous() for c in (lo, hi)]
-    out = ring.ring_attention_forward(ch(q), ch(k), ch(v), causal, exchange=exchange)
+    out = ring.ring_attention_forward(ch(q), ch(k), ch(v), causal, exchange=None if exchange == "default" else exchange)
     torch.cuda.synchronize()
     worst = 0.0
     for o, c in zip(out, (lo, hi)):

@@ -480,7 +480,7 @@ def test_context_parallel_pull_two_gpus_matches_monolithic():
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
                         os.path.join(here, "harness", "ring_check.py"), "2048"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("PASS") == 10 and "FAIL" not in r.stdout
+    assert r.stdout.count("PASS") == 14 and "FAIL" not in r.stdout      # 2 ranks x (pull, sendrecv, default: causal + full; gather: causal)
 
 
 # ---- BF16 operands (flash_attn_fwd_bf16; the reference is FP16 only) ----
