@@ -89,6 +89,9 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // when the kernel drains (watchdog_publish) -- the CTA of the waiter that gave up does; the others never read the word.
 // block-local "a waiter of this CTA gave up": lets the CTA's exit path skip the global read of the record (a ~1 us round trip
 // that would otherwise sit on the tail of every CTA of every launch)
+// (The 16 bytes of static shared memory shift the kernel's dynamic window off its 1024-byte alignment; fa_fwd_kernel's 1 KB of
+// alignment slack absorbs exactly that -- with 16 bytes to spare at D = 128 -- and its entry check refuses to run otherwise.
+// Keeping the word at the end of the dynamic window instead measured the same: profiles/r02_c32_ab_merge2.log.)
 __device__ __forceinline__ unsigned int* watchdog_block_flag() {
     __shared__ unsigned int raised;
     return &raised;
