@@ -76,10 +76,11 @@ constexpr int kTmemCols = 512;
 // Epilogue warpgroup (experiment, -DFA_EPI_WG=1; off in the product build): warps 12-15 drain a finished O tile from TMEM
 // (O / l -> fp16 -> swizzled smem for the TMA store) while the softmax warps are already on the next work item, so an
 // item's epilogue (~2000 cycles: wait for the last PV, 128 columns through registers) leaves the softmax warps' chain.
-// Parity-clean on the whole GPU suite and 4-8 % SLOWER at D=128 (profiles/r02_c14_*): with 512 threads the register file
-// only allows 200/72/40 or 208/56/40 registers for softmax / MMA+producer / epilogue warps (spills in the softmax or the
-// MMA warp), and what the softmax warps gain is small because the next item's first S only exists ~1000 cycles after
-// the item's last PV anyway.
+// Parity-clean on the whole GPU suite and 4-8 % SLOWER at D=128 when first built (profiles/r02_c14_*); on the final kernel
+// level at N=8192 without a mask, -1.2 % with one, -5 % at causal N=2048 (profiles/r02_c33_*; its warps sleeping between
+// polls, -DFA_EPI_SLEEP=ns, changes nothing).  With 512 threads the register file only allows 200/72/40 or 208/56/40
+// registers for softmax / MMA+producer / epilogue warps (spills in the softmax or the MMA warp), and what the softmax warps
+// gain is small because the next item's first S only exists ~1000 cycles after the item's last PV anyway.
 #ifndef FA_EPI_WG
 #define FA_EPI_WG 0
 #endif
@@ -1034,7 +1035,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     const int n_t = t ? wi.n1 : wi.n0;
                     uint32_t& cnt = t ? cnt1 : cnt0;
                     uint32_t& pv = t ? pv1 : pv0;
+#ifdef FA_EPI_SLEEP
+                    mbar_wait_sleepy(bar_epi_full + 8 * t, cnt & 1u, 36 + t, FA_EPI_SLEEP);
+#else
                     mbar_wait(bar_epi_full + 8 * t, cnt & 1u, 36 + t);
+#endif
                     const float l_run = ld_shared_f32(smem_base + C::kMlOffset + (t * kBlockM + row_in_tile) * 4);
                     if (n_t > 0) {
                         pv += (uint32_t)n_t;

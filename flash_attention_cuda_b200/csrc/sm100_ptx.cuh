@@ -128,6 +128,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     }
 }
 
+// mbar_wait for a warp that has a long time to wait and shares its sub-partition with latency-critical warps: sleeps between
+// polls instead of re-issuing try_wait back to back (epilogue warpgroup experiment, -DFA_EPI_WG=1)
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity, int tag, unsigned ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_timer_ns();
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if ((++polls & 63u) == 0u) {
+            if (watchdog_aborted()) return;
+            if (global_timer_ns() - t0 > kWatchdogNs) {
+                watchdog_raise(tag);
+                return;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ clusters / CTA pairs
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
