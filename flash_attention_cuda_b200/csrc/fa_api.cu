@@ -79,7 +79,9 @@ struct DeviceState {
     size_t stage_bytes = 0;
     // three streams (H2D, kernels, D2H) and per-chunk events: the host entry point pipelines head chunks
     cudaStream_t host_stream = nullptr, host_in = nullptr, host_out = nullptr;
+    cudaStream_t host_in2[2] = {nullptr, nullptr};            // K and V travel next to Q on streams of their own
     cudaEvent_t ev_in[kHostChunks] = {}, ev_k[kHostChunks] = {};
+    cudaEvent_t ev_in2[2][kHostChunks] = {};
     bool host_ready = false;
 };
 DeviceState g_dev[kMaxDevices];
@@ -466,18 +468,46 @@ static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const 
     if (chunks > BH) chunks = BH;
     if (chunks < 1) chunks = 1;
     const size_t head_bytes = (size_t)N * D * sizeof(__half);
-    int h0 = 0;
+    // Q, K, V of a chunk travel one after the other on one stream.  FLASH_ATTN_B200_HOST_STREAMS=3 gives each tensor a
+    // stream of its own (the idea: a copy costs ~12 us of set-up on its engine, during which the link idles if nothing else
+    // is in flight) -- measured the same or slower (profiles/r02_c34_host_pipeline.log).  What does pay, 1.5-3 %: the
+    // chunks shrink towards the end of the call (FLASH_ATTN_B200_HOST_TAPER=0: equal chunks), because the last chunk's
+    // kernel and its copy back are the part nothing hides.
+    static const int in_streams = [] { const char* env = getenv("FLASH_ATTN_B200_HOST_STREAMS"); return env && atoi(env) == 3 ? 3 : 1; }();
+    static const bool taper = [] { const char* env = getenv("FLASH_ATTN_B200_HOST_TAPER"); return !(env && atoi(env) == 0); }();
+    // chunk boundaries: equal, or weights chunks+2, chunks+1, ..., 3 (the last chunk ~1/4 of the first)
+    int bound[kHostChunks + 1];
+    bound[0] = 0;
+    {
+        long long wsum = 0, acc = 0;
+        for (int c = 0; c < chunks; c++) wsum += taper ? chunks + 2 - c : 1;
+        for (int c = 0; c < chunks; c++) {
+            acc += taper ? chunks + 2 - c : 1;
+            int b = (int)((long long)BH * acc / wsum);
+            if (b <= bound[c]) b = bound[c] + 1;                  // every chunk carries at least one head (chunks <= BH)
+            if (b > BH - (chunks - 1 - c)) b = BH - (chunks - 1 - c);
+            bound[c + 1] = b;
+        }
+        bound[chunks] = BH;
+    }
     for (int c = 0; c < chunks; c++) {
-        const int h1 = (int)((long long)BH * (c + 1) / chunks);
+        const int h0 = bound[c], h1 = bound[c + 1];
         const int nh = h1 - h0;
         const size_t off = (size_t)h0 * head_bytes, len = (size_t)nh * head_bytes;
         const char *hq8 = static_cast<const char*>(hq), *hk8 = static_cast<const char*>(hk),
                    *hv8 = static_cast<const char*>(hv);
+        cudaStream_t sk = in_streams == 3 ? st->host_in2[0] : st->host_in, sv = in_streams == 3 ? st->host_in2[1] : st->host_in;
         if ((e = cudaMemcpyAsync(dq + off, hq8 + off, len, cudaMemcpyHostToDevice, st->host_in)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemcpyAsync(dk + off, hk8 + off, len, cudaMemcpyHostToDevice, st->host_in)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemcpyAsync(dv + off, hv8 + off, len, cudaMemcpyHostToDevice, st->host_in)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(dk + off, hk8 + off, len, cudaMemcpyHostToDevice, sk)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(dv + off, hv8 + off, len, cudaMemcpyHostToDevice, sv)) != cudaSuccess) return (int)e;
         if ((e = cudaEventRecord(st->ev_in[c], st->host_in)) != cudaSuccess) return (int)e;
         if ((e = cudaStreamWaitEvent(st->host_stream, st->ev_in[c], 0)) != cudaSuccess) return (int)e;
+        if (in_streams == 3) {
+            for (int s2 = 0; s2 < 2; s2++) {
+                if ((e = cudaEventRecord(st->ev_in2[s2][c], st->host_in2[s2])) != cudaSuccess) return (int)e;
+                if ((e = cudaStreamWaitEvent(st->host_stream, st->ev_in2[s2][c], 0)) != cudaSuccess) return (int)e;
+            }
+        }
         int rc = flash_attn_fwd(dq + off, dk + off, dv + off, dout + off, 1, nh, N, D, causal, st->host_stream);   // FA.cu:777
         if (rc != FA_OK) return rc;
         if ((e = cudaEventRecord(st->ev_k[c], st->host_stream)) != cudaSuccess) return (int)e;
@@ -485,7 +515,6 @@ static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const 
         if ((e = cudaMemcpyAsync(static_cast<char*>(ho) + off, dout + off, len, cudaMemcpyDeviceToHost, st->host_out)) !=
             cudaSuccess)
             return (int)e;
-        h0 = h1;
     }
     return (int)cudaStreamSynchronize(st->host_out);
 }
@@ -506,9 +535,13 @@ int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho
         if ((e = cudaStreamCreateWithFlags(&st->host_stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
         if ((e = cudaStreamCreateWithFlags(&st->host_in, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
         if ((e = cudaStreamCreateWithFlags(&st->host_out, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        for (int s2 = 0; s2 < 2; s2++)
+            if ((e = cudaStreamCreateWithFlags(&st->host_in2[s2], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
         for (int i = 0; i < kHostChunks; i++) {
             if ((e = cudaEventCreateWithFlags(&st->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
             if ((e = cudaEventCreateWithFlags(&st->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+            for (int s2 = 0; s2 < 2; s2++)
+                if ((e = cudaEventCreateWithFlags(&st->ev_in2[s2][i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
         }
         st->host_ready = true;
     }
@@ -524,6 +557,7 @@ int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho
         // an error in the middle of the chunk loop leaves copies and kernels queued on the cached staging buffer
         // (and on the caller's host memory): nothing may still be in flight when the caller sees the error
         cudaStreamSynchronize(st->host_in);
+        for (int s2 = 0; s2 < 2; s2++) cudaStreamSynchronize(st->host_in2[s2]);
         cudaStreamSynchronize(st->host_stream);
         cudaStreamSynchronize(st->host_out);
         return rc;
@@ -619,11 +653,19 @@ void flash_attn_destroy(void) {
         if (st->stage) cudaFree(st->stage);
         if (st->host_stream) cudaStreamDestroy(st->host_stream);
         if (st->host_in) cudaStreamDestroy(st->host_in);
+        for (int s2 = 0; s2 < 2; s2++) {
+            if (st->host_in2[s2]) cudaStreamDestroy(st->host_in2[s2]);
+            st->host_in2[s2] = nullptr;
+        }
         if (st->host_out) cudaStreamDestroy(st->host_out);
         for (int i = 0; i < kHostChunks; i++) {
             if (st->ev_in[i]) cudaEventDestroy(st->ev_in[i]);
             if (st->ev_k[i]) cudaEventDestroy(st->ev_k[i]);
             st->ev_in[i] = st->ev_k[i] = nullptr;
+            for (int s2 = 0; s2 < 2; s2++) {
+                if (st->ev_in2[s2][i]) cudaEventDestroy(st->ev_in2[s2][i]);
+                st->ev_in2[s2][i] = nullptr;
+            }
         }
         st->stage = nullptr;
         st->stage_bytes = 0;
