@@ -42,7 +42,8 @@ std::once_flag g_encode_once;
 EncodeTiledFn g_encode = nullptr;
 
 constexpr int kCaptureSlots = 1024;  // scheduler words reserved for launches recorded into CUDA graphs (one each, never reused)
-constexpr int kTmapCache = 8;        // cached descriptor sets per device (flash_attn_fwd re-encodes nothing for a repeated call)
+constexpr int kTmapCache = 16;       // cached descriptor sets per device (flash_attn_fwd re-encodes nothing for a repeated call;
+                                     // flash_attn_fwd_host alone cycles through 8 of them, one per head chunk)
 
 struct TmapSet {
     const void *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr;
