@@ -8,6 +8,7 @@
 #include "../../include/flash_attn.h"
 
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -20,6 +21,12 @@ constexpr int kMaxDevices = 64;
 constexpr int kSchedSlots = 4096;
 constexpr int kHostChunks = 32;    // most head chunks flash_attn_fwd_host can pipeline over PCIe (events are per chunk)
 constexpr int kHostChunksDefault = 8;   // FLASH_ATTN_B200_HOST_CHUNKS overrides (A/B runs)
+#ifndef FA_HOST_FIRST_DEFAULT
+#define FA_HOST_FIRST_DEFAULT 0
+#endif
+#ifndef FA_HOST_ZEROCOPY_DEFAULT
+#define FA_HOST_ZEROCOPY_DEFAULT 1
+#endif
 constexpr int kGroupMB = 32;       // K+V bytes of one scheduling group of heads (make_params)
 // exp2 on the FMA pipe (fa::poly_pair): share of element pairs for D = 128 with >= 32 KV tiles / for D = 64.
 // Build-time so that A/B variants are one -D away; the defaults are the measured optimum (profiles/).
@@ -446,6 +453,9 @@ int flash_attn_merge(const float* o_partial, const float* ml, void* o, int split
     return (int)cudaGetLastError();
 }
 
+static std::atomic<int> g_host_first{-1};         // -1: read FLASH_ATTN_B200_HOST_FIRST once; 0: plain taper; w > 0: weight of the first chunk
+static std::atomic<int> g_host_zerocopy{-1};      // -1: read FLASH_ATTN_B200_HOST_ZEROCOPY once; 0 / 1: staged / direct O store
+
 // Body of flash_attn_fwd_host once the streams, events and the staging buffer exist.
 static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const void* hv, void* ho, int BH, int N, int D,
                          int causal, size_t bytes) {
@@ -476,20 +486,57 @@ static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const 
     // kernel and its copy back are the part nothing hides.
     static const int in_streams = [] { const char* env = getenv("FLASH_ATTN_B200_HOST_STREAMS"); return env && atoi(env) == 3 ? 3 : 1; }();
     static const bool taper = [] { const char* env = getenv("FLASH_ATTN_B200_HOST_TAPER"); return !(env && atoi(env) == 0); }();
+    // FLASH_ATTN_B200_HOST_ZEROCOPY=1: when the caller's O buffer is pinned and mapped into the device's address space, the
+    // kernel's epilogue TMA-stores the finished O tiles straight into it -- the copy back is part of the kernel, there is no
+    // staging buffer for O, no D2H copy and no copy engine behind the last kernel.  Pageable buffers keep the staged path.
+    int zc_mode = g_host_zerocopy.load(std::memory_order_relaxed);      // flash_attn_debug_set_host_zerocopy (tests, A/B runs)
+    if (zc_mode < 0) {
+        const char* env = getenv("FLASH_ATTN_B200_HOST_ZEROCOPY");
+        zc_mode = env ? atoi(env) : FA_HOST_ZEROCOPY_DEFAULT;
+        g_host_zerocopy.store(zc_mode, std::memory_order_relaxed);
+    }
+    char* o_direct = nullptr;
+    if (zc_mode == 1) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, ho) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+            o_direct = static_cast<char*>(pa.devicePointer);
+        else
+            cudaGetLastError();       // pageable memory is not an error here
+    }
     // chunk boundaries: equal, or weights chunks+2, chunks+1, ..., 3 (the last chunk ~1/4 of the first)
     int bound[kHostChunks + 1];
     bound[0] = 0;
     {
+        // FLASH_ATTN_B200_HOST_FIRST=w (A/B runs): weight of the first chunk -- until its kernel starts nothing flows back
+        int first_w = g_host_first.load(std::memory_order_relaxed);      // flash_attn_debug_set_host_first (A/B runs)
+        if (first_w < 0) {
+            const char* env = getenv("FLASH_ATTN_B200_HOST_FIRST");
+            first_w = env ? atoi(env) : FA_HOST_FIRST_DEFAULT;
+            g_host_first.store(first_w, std::memory_order_relaxed);
+        }
+        auto weight = [&](int c) -> long long { return !taper ? 1 : (c == 0 && first_w > 0) ? first_w : chunks + 2 - c; };
         long long wsum = 0, acc = 0;
-        for (int c = 0; c < chunks; c++) wsum += taper ? chunks + 2 - c : 1;
+        for (int c = 0; c < chunks; c++) wsum += weight(c);
         for (int c = 0; c < chunks; c++) {
-            acc += taper ? chunks + 2 - c : 1;
+            acc += weight(c);
             int b = (int)((long long)BH * acc / wsum);
             if (b <= bound[c]) b = bound[c] + 1;                  // every chunk carries at least one head (chunks <= BH)
             if (b > BH - (chunks - 1 - c)) b = BH - (chunks - 1 - c);
             bound[c + 1] = b;
         }
         bound[chunks] = BH;
+    }
+    // FLASH_ATTN_B200_HOST_TRACE=1: device timestamps of every chunk's three stages (last H2D byte, kernel start / end, last
+    // D2H byte) relative to the call's first copy, printed to stderr after the call -- where the call's time goes
+    // (tests/harness/host_trace.py).  Timing events exist only in this mode.
+    static const bool trace = [] { const char* env = getenv("FLASH_ATTN_B200_HOST_TRACE"); return env && atoi(env) == 1; }();
+    cudaEvent_t tr_start = nullptr, tr_in[kHostChunks] = {}, tr_k0[kHostChunks] = {}, tr_k1[kHostChunks] = {}, tr_out[kHostChunks] = {};
+    if (trace) {
+        cudaEventCreate(&tr_start);
+        for (int c = 0; c < chunks; c++) {
+            cudaEventCreate(&tr_in[c]); cudaEventCreate(&tr_k0[c]); cudaEventCreate(&tr_k1[c]); cudaEventCreate(&tr_out[c]);
+        }
+        cudaEventRecord(tr_start, st->host_in);
     }
     for (int c = 0; c < chunks; c++) {
         const int h0 = bound[c], h1 = bound[c + 1];
@@ -509,15 +556,37 @@ static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const 
                 if ((e = cudaStreamWaitEvent(st->host_stream, st->ev_in2[s2][c], 0)) != cudaSuccess) return (int)e;
             }
         }
-        int rc = flash_attn_fwd(dq + off, dk + off, dv + off, dout + off, 1, nh, N, D, causal, st->host_stream);   // FA.cu:777
+        if (trace) { cudaEventRecord(tr_in[c], st->host_in); cudaEventRecord(tr_k0[c], st->host_stream); }
+        int rc = flash_attn_fwd(dq + off, dk + off, dv + off, o_direct ? o_direct + off : dout + off, 1, nh, N, D, causal,
+                                st->host_stream);   // FA.cu:777
         if (rc != FA_OK) return rc;
+        if (trace) cudaEventRecord(tr_k1[c], st->host_stream);
+        if (o_direct) {
+            if (trace) cudaEventRecord(tr_out[c], st->host_stream);
+            continue;
+        }
         if ((e = cudaEventRecord(st->ev_k[c], st->host_stream)) != cudaSuccess) return (int)e;
         if ((e = cudaStreamWaitEvent(st->host_out, st->ev_k[c], 0)) != cudaSuccess) return (int)e;
         if ((e = cudaMemcpyAsync(static_cast<char*>(ho) + off, dout + off, len, cudaMemcpyDeviceToHost, st->host_out)) !=
             cudaSuccess)
             return (int)e;
+        if (trace) cudaEventRecord(tr_out[c], st->host_out);
     }
-    return (int)cudaStreamSynchronize(st->host_out);
+    e = cudaStreamSynchronize(o_direct ? st->host_stream : st->host_out);
+    if (trace) {
+        fprintf(stderr, "host_trace chunks=%d (ms after the first copy was queued: heads | H2D done | kernel start, end | D2H done)\n", chunks);
+        for (int c = 0; c < chunks; c++) {
+            float a = 0.f, b = 0.f, k1 = 0.f, d = 0.f;
+            cudaEventElapsedTime(&a, tr_start, tr_in[c]);
+            cudaEventElapsedTime(&b, tr_start, tr_k0[c]);
+            cudaEventElapsedTime(&k1, tr_start, tr_k1[c]);
+            cudaEventElapsedTime(&d, tr_start, tr_out[c]);
+            fprintf(stderr, "host_trace %2d: %2d | %.3f | %.3f %.3f | %.3f\n", c, bound[c + 1] - bound[c], a, b, k1, d);
+            cudaEventDestroy(tr_in[c]); cudaEventDestroy(tr_k0[c]); cudaEventDestroy(tr_k1[c]); cudaEventDestroy(tr_out[c]);
+        }
+        cudaEventDestroy(tr_start);
+    }
+    return (int)e;
 }
 
 int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho, int B, int H, int N, int D,
@@ -783,6 +852,9 @@ extern "C" int flash_attn_debug_tiles_per_item(int D) {
 }
 // -1 automatic (use_split), 0 never, 1 always: which work decomposition flash_attn_fwd uses from now on (A/B runs, tests)
 extern "C" void flash_attn_debug_set_split(int mode) { g_split_override.store(mode < -1 || mode > 1 ? -1 : mode, std::memory_order_relaxed); }
+// 0: flash_attn_fwd_host copies O back with a copy engine; 1: the kernel stores O straight into a pinned, mapped host buffer
+extern "C" void flash_attn_debug_set_host_zerocopy(int mode) { g_host_zerocopy.store(mode ? 1 : 0, std::memory_order_relaxed); }
+extern "C" void flash_attn_debug_set_host_first(int w) { g_host_first.store(w < 0 ? 0 : w, std::memory_order_relaxed); }
 // 1 when flash_attn_fwd would run this shape in split mode on the current device
 extern "C" int flash_attn_debug_uses_split(int B, int H, int N, int causal) {
     int err = 0;

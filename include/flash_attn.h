@@ -85,7 +85,10 @@ int flash_attn_merge(const float* o_partial, const float* ml, void* o, int split
                      void* stream);
 
 /* The reference harness's call pattern with HOST buffers (FA.cu:771-780): H2D of Q,K,V,
- * dispatch, D2H of O, on a per-device cached staging workspace.  Blocks until O is on the host. */
+ * dispatch, D2H of O, on a per-device cached staging workspace, pipelined over head chunks.  When `ho` is pinned and
+ * mapped (cudaHostAlloc / cudaHostRegister), the kernel's epilogue stores the O tiles straight into it with TMA -- no
+ * staging of O, no D2H copy; pageable `ho` is copied back from the staging buffer.  FLASH_ATTN_B200_HOST_ZEROCOPY=0
+ * forces the copy.  Blocks until O is on the host. */
 int flash_attn_fwd_host(const void* hq, const void* hk, const void* hv, void* ho, int B, int H, int N,
                         int D, int causal);
 
