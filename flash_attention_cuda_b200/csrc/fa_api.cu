@@ -453,6 +453,31 @@ int flash_attn_merge(const float* o_partial, const float* ml, void* o, int split
     return (int)cudaGetLastError();
 }
 
+// Head chunks of one flash_attn_fwd_host call: bound[0] = 0 < bound[1] < ... < bound[chunks] = BH.  A chunk should carry
+// enough bytes to amortise its copies, events and launch (>= 16 MiB of input), every chunk carries at least one head, and with
+// `taper` the chunks shrink towards the end of the call (weights chunks+2, chunks+1, ..., 3: the last ~1/4 of the first)
+// because the last chunk's kernel and its way back are the part nothing hides; first_w > 0 replaces the first weight.
+static int host_chunk_bounds(int BH, size_t bytes, int want_chunks, bool taper, int first_w, int* bound) {
+    int chunks = (int)((3 * bytes) >> 24);
+    if (chunks > want_chunks) chunks = want_chunks;
+    if (chunks > kHostChunks) chunks = kHostChunks;
+    if (chunks > BH) chunks = BH;
+    if (chunks < 1) chunks = 1;
+    auto weight = [&](int c) -> long long { return !taper ? 1 : (c == 0 && first_w > 0) ? first_w : chunks + 2 - c; };
+    long long wsum = 0, acc = 0;
+    for (int c = 0; c < chunks; c++) wsum += weight(c);
+    bound[0] = 0;
+    for (int c = 0; c < chunks; c++) {
+        acc += weight(c);
+        int b = (int)((long long)BH * acc / wsum);
+        if (b <= bound[c]) b = bound[c] + 1;                  // every chunk carries at least one head (chunks <= BH)
+        if (b > BH - (chunks - 1 - c)) b = BH - (chunks - 1 - c);
+        bound[c + 1] = b;
+    }
+    bound[chunks] = BH;
+    return chunks;
+}
+
 static std::atomic<int> g_host_first{-1};         // -1: read FLASH_ATTN_B200_HOST_FIRST once; 0: plain taper; w > 0: weight of the first chunk
 static std::atomic<int> g_host_zerocopy{-1};      // -1: read FLASH_ATTN_B200_HOST_ZEROCOPY once; 0 / 1: staged / direct O store
 
@@ -473,11 +498,16 @@ static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const 
         const int v = env ? atoi(env) : 0;
         return v >= 1 && v <= kHostChunks ? v : kHostChunksDefault;
     }();
-    // a chunk should carry enough bytes to amortise its three copies, two events and one launch: >= 16 MiB of input
-    int chunks = (int)((3 * bytes) >> 24);
-    if (chunks > want_chunks) chunks = want_chunks;
-    if (chunks > BH) chunks = BH;
-    if (chunks < 1) chunks = 1;
+    // FLASH_ATTN_B200_HOST_FIRST=w (A/B runs): weight of the first chunk -- until its kernel starts nothing flows back
+    int first_w = g_host_first.load(std::memory_order_relaxed);      // flash_attn_debug_set_host_first (A/B runs)
+    if (first_w < 0) {
+        const char* env = getenv("FLASH_ATTN_B200_HOST_FIRST");
+        first_w = env ? atoi(env) : FA_HOST_FIRST_DEFAULT;
+        g_host_first.store(first_w, std::memory_order_relaxed);
+    }
+    static const bool taper = [] { const char* env = getenv("FLASH_ATTN_B200_HOST_TAPER"); return !(env && atoi(env) == 0); }();
+    int bound[kHostChunks + 1];
+    const int chunks = host_chunk_bounds(BH, bytes, want_chunks, taper, first_w, bound);
     const size_t head_bytes = (size_t)N * D * sizeof(__half);
     // Q, K, V of a chunk travel one after the other on one stream.  FLASH_ATTN_B200_HOST_STREAMS=3 gives each tensor a
     // stream of its own (the idea: a copy costs ~12 us of set-up on its engine, during which the link idles if nothing else
@@ -485,7 +515,6 @@ static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const 
     // chunks shrink towards the end of the call (FLASH_ATTN_B200_HOST_TAPER=0: equal chunks), because the last chunk's
     // kernel and its copy back are the part nothing hides.
     static const int in_streams = [] { const char* env = getenv("FLASH_ATTN_B200_HOST_STREAMS"); return env && atoi(env) == 3 ? 3 : 1; }();
-    static const bool taper = [] { const char* env = getenv("FLASH_ATTN_B200_HOST_TAPER"); return !(env && atoi(env) == 0); }();
     // FLASH_ATTN_B200_HOST_ZEROCOPY=1: when the caller's O buffer is pinned and mapped into the device's address space, the
     // kernel's epilogue TMA-stores the finished O tiles straight into it -- the copy back is part of the kernel, there is no
     // staging buffer for O, no D2H copy and no copy engine behind the last kernel.  Pageable buffers keep the staged path.
@@ -503,32 +532,9 @@ static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const 
         else
             cudaGetLastError();       // pageable memory is not an error here
     }
-    // chunk boundaries: equal, or weights chunks+2, chunks+1, ..., 3 (the last chunk ~1/4 of the first)
-    int bound[kHostChunks + 1];
-    bound[0] = 0;
-    {
-        // FLASH_ATTN_B200_HOST_FIRST=w (A/B runs): weight of the first chunk -- until its kernel starts nothing flows back
-        int first_w = g_host_first.load(std::memory_order_relaxed);      // flash_attn_debug_set_host_first (A/B runs)
-        if (first_w < 0) {
-            const char* env = getenv("FLASH_ATTN_B200_HOST_FIRST");
-            first_w = env ? atoi(env) : FA_HOST_FIRST_DEFAULT;
-            g_host_first.store(first_w, std::memory_order_relaxed);
-        }
-        auto weight = [&](int c) -> long long { return !taper ? 1 : (c == 0 && first_w > 0) ? first_w : chunks + 2 - c; };
-        long long wsum = 0, acc = 0;
-        for (int c = 0; c < chunks; c++) wsum += weight(c);
-        for (int c = 0; c < chunks; c++) {
-            acc += weight(c);
-            int b = (int)((long long)BH * acc / wsum);
-            if (b <= bound[c]) b = bound[c] + 1;                  // every chunk carries at least one head (chunks <= BH)
-            if (b > BH - (chunks - 1 - c)) b = BH - (chunks - 1 - c);
-            bound[c + 1] = b;
-        }
-        bound[chunks] = BH;
-    }
     // FLASH_ATTN_B200_HOST_TRACE=1: device timestamps of every chunk's three stages (last H2D byte, kernel start / end, last
     // D2H byte) relative to the call's first copy, printed to stderr after the call -- where the call's time goes
-    // (tests/harness/host_trace.py).  Timing events exist only in this mode.
+    // (profiles/r02_c40_host_trace.log).  Timing events exist only in this mode.
     static const bool trace = [] { const char* env = getenv("FLASH_ATTN_B200_HOST_TRACE"); return env && atoi(env) == 1; }();
     cudaEvent_t tr_start = nullptr, tr_in[kHostChunks] = {}, tr_k0[kHostChunks] = {}, tr_k1[kHostChunks] = {}, tr_out[kHostChunks] = {};
     if (trace) {
@@ -854,6 +860,11 @@ extern "C" int flash_attn_debug_tiles_per_item(int D) {
 extern "C" void flash_attn_debug_set_split(int mode) { g_split_override.store(mode < -1 || mode > 1 ? -1 : mode, std::memory_order_relaxed); }
 // 0: flash_attn_fwd_host copies O back with a copy engine; 1: the kernel stores O straight into a pinned, mapped host buffer
 extern "C" void flash_attn_debug_set_host_zerocopy(int mode) { g_host_zerocopy.store(mode ? 1 : 0, std::memory_order_relaxed); }
+// Test hook: the head-chunk boundaries flash_attn_fwd_host would use (bound must hold 33 ints); returns the chunk count
+extern "C" int flash_attn_debug_host_chunks(int BH, long long bytes_per_tensor, int want_chunks, int taper, int first_w, int* bound) {
+    if (!bound || BH < 1 || bytes_per_tensor < 1 || want_chunks < 1) return FA_ERR_BAD_SHAPE;
+    return host_chunk_bounds(BH, (size_t)bytes_per_tensor, want_chunks, taper != 0, first_w, bound);
+}
 extern "C" void flash_attn_debug_set_host_first(int w) { g_host_first.store(w < 0 ? 0 : w, std::memory_order_relaxed); }
 // 1 when flash_attn_fwd would run this shape in split mode on the current device
 extern "C" int flash_attn_debug_uses_split(int B, int H, int N, int causal) {
