@@ -24,6 +24,9 @@ constexpr int kHostChunksDefault = 8;   // FLASH_ATTN_B200_HOST_CHUNKS overrides
 #ifndef FA_HOST_FIRST_DEFAULT
 #define FA_HOST_FIRST_DEFAULT 0
 #endif
+#ifndef FA_HOST_CTAS_DEFAULT
+#define FA_HOST_CTAS_DEFAULT 0
+#endif
 #ifndef FA_HOST_ZEROCOPY_DEFAULT
 #define FA_HOST_ZEROCOPY_DEFAULT 1
 #endif
@@ -252,8 +255,9 @@ fa::Params make_params(int BH, int Nq, int Nkv, int D, int causal, long long shi
 
 template <int D, int kPoly, bool kBF16 = false>
 int launch(DeviceState* st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-           const CUtensorMap& to, fa::Params p, cudaStream_t stream) {
+           const CUtensorMap& to, fa::Params p, cudaStream_t stream, int max_ctas = 0) {
     int avail = st->num_sms - g_sm_margin.load(std::memory_order_relaxed);
+    if (max_ctas > 0 && avail > max_ctas) avail = max_ctas;     // a deliberately narrow grid (flash_attn_fwd_host)
     if (avail < 1) avail = 1;
     int grid = p.total_work < avail ? p.total_work : avail;
     if (grid < 1) grid = 1;
@@ -324,7 +328,7 @@ int get_tmaps(DeviceState* st, const void* q, const void* k, const void* v, cons
 }
 
 int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaStream_t stream, bool bf16 = false,
-        long long kv_head_rows = 0) {
+        long long kv_head_rows = 0, int max_ctas = 0) {
     int err = 0;
     DeviceState* st = device_state(&err);
     if (!st) return err;
@@ -335,28 +339,35 @@ int run(const void* q, const void* k, const void* v, fa::Params& p, int D, cudaS
     if (rc != FA_OK) return rc;
     const bool poly = use_poly(D, p.Nkv, p.causal);
     if (bf16) {
-        if (D == 64) return launch<64, kPolyD64, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
+        if (D == 64) return launch<64, kPolyD64, true>(st, t.tq, t.tk, t.tv, t.to, p, stream, max_ctas);
         return poly ? launch<128, kPolyLong, true>(st, t.tq, t.tk, t.tv, t.to, p, stream)
-                    : launch<128, 0, true>(st, t.tq, t.tk, t.tv, t.to, p, stream);
+                    : launch<128, 0, true>(st, t.tq, t.tk, t.tv, t.to, p, stream, max_ctas);
     }
-    if (D == 64) return launch<64, kPolyD64>(st, t.tq, t.tk, t.tv, t.to, p, stream);
+    if (D == 64) return launch<64, kPolyD64>(st, t.tq, t.tk, t.tv, t.to, p, stream, max_ctas);
     return poly ? launch<128, kPolyLong>(st, t.tq, t.tk, t.tv, t.to, p, stream)
-                : launch<128, 0>(st, t.tq, t.tk, t.tv, t.to, p, stream);
+                : launch<128, 0>(st, t.tq, t.tk, t.tv, t.to, p, stream, max_ctas);
 }
 
 }  // namespace
 
 extern "C" {
 
-int flash_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int H, int N, int D, int causal,
-                   void* stream) {
+// flash_attn_fwd on at most max_ctas CTAs (0 = every SM).  Same work items, same arithmetic, same bits: the persistent
+// CTAs just claim more items each.
+static int fwd_on_ctas(const void* q, const void* k, const void* v, void* o, int B, int H, int N, int D, int causal,
+                       void* stream, int max_ctas) {
     int rc = validate(q, k, v, o, B, H, N, N, D);
     if (rc != FA_OK) return rc;
     DeviceState* st = device_state(&rc);
     if (!st) return rc;
     fa::Params p = make_params(B * H, N, N, D, causal, 0, use_split(B * H, N, causal, st->num_sms));
     p.o = static_cast<__half*>(o);
-    return run(q, k, v, p, D, static_cast<cudaStream_t>(stream));
+    return run(q, k, v, p, D, static_cast<cudaStream_t>(stream), /*bf16=*/false, /*kv_head_rows=*/0, max_ctas);
+}
+
+int flash_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int H, int N, int D, int causal,
+                   void* stream) {
+    return fwd_on_ctas(q, k, v, o, B, H, N, D, causal, stream, 0);
 }
 
 int flash_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, int B, int H, int N, int D, int causal,
@@ -480,6 +491,7 @@ static int host_chunk_bounds(int BH, size_t bytes, int want_chunks, bool taper, 
 
 static std::atomic<int> g_host_first{-1};         // -1: read FLASH_ATTN_B200_HOST_FIRST once; 0: plain taper; w > 0: weight of the first chunk
 static std::atomic<int> g_host_zerocopy{-1};      // -1: read FLASH_ATTN_B200_HOST_ZEROCOPY once; 0 / 1: staged / direct O store
+static std::atomic<int> g_host_ctas{-1};          // -1: read FLASH_ATTN_B200_HOST_CTAS once; 0: every SM; n > 0: CTAs of a chunk's kernel under the direct store
 
 // Body of flash_attn_fwd_host once the streams, events and the staging buffer exist.
 static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const void* hv, void* ho, int BH, int N, int D,
@@ -524,6 +536,13 @@ static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const 
         zc_mode = env ? atoi(env) : FA_HOST_ZEROCOPY_DEFAULT;
         g_host_zerocopy.store(zc_mode, std::memory_order_relaxed);
     }
+    int host_ctas = g_host_ctas.load(std::memory_order_relaxed);        // flash_attn_debug_set_host_ctas (A/B runs)
+    if (host_ctas < 0) {
+        const char* env = getenv("FLASH_ATTN_B200_HOST_CTAS");
+        host_ctas = env ? atoi(env) : FA_HOST_CTAS_DEFAULT;
+        if (host_ctas < 0) host_ctas = 0;
+        g_host_ctas.store(host_ctas, std::memory_order_relaxed);
+    }
     char* o_direct = nullptr;
     if (zc_mode == 1) {
         cudaPointerAttributes pa;
@@ -563,8 +582,15 @@ static int host_pipeline(DeviceState* st, const void* hq, const void* hk, const 
             }
         }
         if (trace) { cudaEventRecord(tr_in[c], st->host_in); cudaEventRecord(tr_k0[c], st->host_stream); }
-        int rc = flash_attn_fwd(dq + off, dk + off, dv + off, o_direct ? o_direct + off : dout + off, 1, nh, N, D, causal,
-                                st->host_stream);   // FA.cu:777
+        // With the direct store the kernel IS the way back, and PCIe carries its writes upstream next to the read requests
+        // of the H2D copies: a kernel on every SM emits O as fast as the link takes it and the copies in fall from 54 to
+        // ~35 GB/s while it runs (profiles/r02_c41_host_trace_zerocopy.log).  FLASH_ATTN_B200_HOST_CTAS=n (A/B switch, off by
+        // default) runs every chunk's kernel but the last on n CTAs, stretching it over the next chunk's way in so that O
+        // trickles back instead: bit-identical output and the SAME call time for n = 64 ... 14 (4.206-4.212 ms,
+        // profiles/r02_c48_host_ab_ctas.log) -- the link charges the bytes of either direction whenever they travel.
+        const int lim = (o_direct && c + 1 < chunks) ? host_ctas : 0;
+        int rc = fwd_on_ctas(dq + off, dk + off, dv + off, o_direct ? o_direct + off : dout + off, 1, nh, N, D, causal,
+                             st->host_stream, lim);   // FA.cu:777
         if (rc != FA_OK) return rc;
         if (trace) cudaEventRecord(tr_k1[c], st->host_stream);
         if (o_direct) {
@@ -865,6 +891,7 @@ extern "C" int flash_attn_debug_host_chunks(int BH, long long bytes_per_tensor, 
     if (!bound || BH < 1 || bytes_per_tensor < 1 || want_chunks < 1) return FA_ERR_BAD_SHAPE;
     return host_chunk_bounds(BH, (size_t)bytes_per_tensor, want_chunks, taper != 0, first_w, bound);
 }
+extern "C" void flash_attn_debug_set_host_ctas(int n) { g_host_ctas.store(n < 0 ? 0 : n, std::memory_order_relaxed); }
 extern "C" void flash_attn_debug_set_host_first(int w) { g_host_first.store(w < 0 ? 0 : w, std::memory_order_relaxed); }
 // 1 when flash_attn_fwd would run this shape in split mode on the current device
 extern "C" int flash_attn_debug_uses_split(int B, int H, int N, int causal) {
